@@ -1,0 +1,121 @@
+"""ctypes binding of libibgs_b200.so (the C ABI in include/ibgs_b200.h).
+
+There is NO fallback: if the shared library is missing or does not load, importing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libibgs_b200.so")
+
+IBGS_BUF_GEOM, IBGS_BUF_BINNING, IBGS_BUF_IMAGE, IBGS_BUF_SCRATCH = 0, 1, 2, 3
+MAX_SRC = 5
+MAX_BUFFER_LENGTH = 8
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
+
+_fp = C.c_void_p  # all data pointers travel as raw addresses
+
+
+class IbgsView(C.Structure):
+    _fields_ = [
+        ("image_height", C.c_int32), ("image_width", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("nb_src_images", C.c_int32), ("buffer_length", C.c_int32),
+        ("depth_error_threshold", C.c_float),
+        ("prefiltered", C.c_int32), ("render_geo", C.c_int32), ("render_depth_only", C.c_int32),
+        ("debug", C.c_int32),
+        ("bg", _fp), ("viewmatrix", _fp), ("projmatrix", _fp), ("campos", _fp),
+        ("ref_to_src_list", _fp), ("src_cam_pos", _fp), ("src_images", _fp), ("src_rendered_depths", _fp),
+    ]
+
+
+class IbgsForwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("view", IbgsView),
+        ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp), ("scales", _fp),
+        ("rotations", _fp), ("cov3D_precomp", _fp), ("all_map", _fp),
+        ("out_color", _fp), ("radii", _fp), ("out_normal_map", _fp), ("out_median_intersected_depth", _fp),
+        ("out_cam_feat", _fp), ("out_warped_image", _fp), ("out_min_depth_diff", _fp),
+        ("out_camera_ray", _fp), ("out_use_first_src_frame", _fp),
+        ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p),
+        ("tex_generation_out", C.c_int64),
+    ]
+
+
+class IbgsBackwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("R", C.c_int64), ("view", IbgsView),
+        ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("scales", _fp), ("rotations", _fp),
+        ("cov3D_precomp", _fp), ("all_map", _fp), ("radii", _fp),
+        ("out_median_intersected_depth", _fp), ("out_warped_image", _fp),
+        ("geom_buffer", _fp), ("binning_buffer", _fp), ("image_buffer", _fp),
+        ("tex_generation", C.c_int64),
+        ("dL_dout_color", _fp), ("dL_dout_normal_map", _fp), ("dL_dout_median_intersected_depth", _fp),
+        ("dL_dout_warped_image", _fp),
+        ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dmeans2D_abs", _fp), ("dL_dcolors", _fp),
+        ("dL_dopacity", _fp), ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscales", _fp),
+        ("dL_drotations", _fp), ("dL_dall_map", _fp),
+        ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p),
+    ]
+
+
+EXPORTS = [
+    "ibgs_forward", "ibgs_backward", "ibgs_mark_visible", "ibgs_dist2_scratch_bytes", "ibgs_dist2",
+    "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
+    "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached",
+]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m ibgs_b200.build` "
+            "(there is deliberately no CPU / PyTorch fallback for the rasterizer)")
+    lib = C.CDLL(LIB_PATH)
+    lib.ibgs_forward.restype = C.c_int64
+    lib.ibgs_forward.argtypes = [C.POINTER(IbgsForwardArgs), C.c_void_p]
+    lib.ibgs_backward.restype = C.c_int
+    lib.ibgs_backward.argtypes = [C.POINTER(IbgsBackwardArgs), C.c_void_p]
+    lib.ibgs_mark_visible.restype = C.c_int
+    lib.ibgs_mark_visible.argtypes = [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]
+    lib.ibgs_dist2_scratch_bytes.restype = C.c_size_t
+    lib.ibgs_dist2_scratch_bytes.argtypes = [C.c_int32]
+    lib.ibgs_dist2.restype = C.c_int
+    lib.ibgs_dist2.argtypes = [C.c_int32, _fp, _fp, _fp, C.c_size_t, C.c_void_p]
+    lib.ibgs_forward_h.restype = C.c_int64
+    lib.ibgs_forward_h.argtypes = [C.POINTER(IbgsForwardArgs)]
+    lib.ibgs_dist2_h.restype = C.c_int
+    lib.ibgs_dist2_h.argtypes = [C.c_int32, _fp, _fp]
+    lib.ibgs_state_layout.restype = C.c_int
+    lib.ibgs_state_layout.argtypes = [C.c_int, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.c_int,
+                                      C.POINTER(C.c_size_t)]
+    lib.ibgs_sort_bits.restype = C.c_int
+    lib.ibgs_sort_bits.argtypes = [C.c_int32]
+    lib.ibgs_last_error.restype = C.c_char_p
+    lib.ibgs_last_error.argtypes = []
+    lib.ibgs_abi_version.restype = C.c_int
+    lib.ibgs_launch_count.restype = C.c_int64
+    lib.ibgs_release_cached.restype = None
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    return lib.ibgs_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc < 0:
+        raise RuntimeError(f"{what} failed ({rc}): {last_error()}")
+    return rc
+
+
+def state_layout(which, count, aux=0):
+    offs = (C.c_size_t * 16)()
+    total = C.c_size_t(0)
+    n = check(lib.ibgs_state_layout(which, count, aux, offs, 16, C.byref(total)), "ibgs_state_layout")
+    return [int(offs[i]) for i in range(n)], int(total.value)

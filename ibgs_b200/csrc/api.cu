@@ -1,0 +1,250 @@
+// api.cu -- extern "C" entry points declared in include/ibgs_b200.h.
+//
+// Orchestration counterpart of CudaRasterizer::Rasterizer::{forward,backward,markVisible}
+// (cuda_rasterizer/rasterizer_impl.cu:258-270,320-515,519-666).  Differences from the reference
+// orchestration: every launch goes to the caller's stream; no cudaMalloc / cudaFree /
+// cudaDeviceSynchronize on the path (the reference does all three per call for its textures,
+// :80-99,135-148); the single unavoidable host read -- num_rendered, which sizes the binning buffers
+// (:429-434) -- is an async copy into pinned memory followed by a stream (not device) synchronise.
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+long long g_launch_count = 0;
+
+namespace {
+thread_local char g_err[1024] = "";
+int32_t* g_pinned_count = nullptr;  // pinned host word for the num_rendered read-back
+}  // namespace
+
+void ibgs_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* ibgs_last_error(void) { return g_err; }
+extern "C" int ibgs_abi_version(void) { return IBGS_ABI_VERSION; }
+extern "C" int64_t ibgs_launch_count(void) { return g_launch_count; }
+extern "C" void ibgs_release_cached(void) {
+  textures_release_all();
+  if (g_pinned_count) {
+    cudaFreeHost(g_pinned_count);
+    g_pinned_count = nullptr;
+  }
+}
+
+static int check_view(const IbgsView& v, bool need_src) {
+  if (v.image_width <= 0 || v.image_height <= 0) {
+    ibgs_set_error("image size must be positive, got %dx%d", v.image_width, v.image_height);
+    return IBGS_EINVAL;
+  }
+  if (!v.bg || !v.viewmatrix || !v.projmatrix || !v.campos) {
+    ibgs_set_error("bg / viewmatrix / projmatrix / campos must not be NULL");
+    return IBGS_EINVAL;
+  }
+  if (v.buffer_length < 1 || v.buffer_length > MAX_BL) {
+    ibgs_set_error("buffer_length must be in [1,%d], got %d", MAX_BL, v.buffer_length);
+    return IBGS_EINVAL;
+  }
+  if (v.nb_src_images < 0 || v.nb_src_images > MAX_SRC) {
+    ibgs_set_error("nb_src_images must be in [0,%d], got %d", MAX_SRC, v.nb_src_images);
+    return IBGS_EINVAL;
+  }
+  if (need_src && v.nb_src_images > 0 &&
+      (!v.ref_to_src_list || !v.src_cam_pos || !v.src_images || !v.src_rendered_depths)) {
+    ibgs_set_error("render_geo needs ref_to_src_list / src_cam_pos / src_images / src_rendered_depths");
+    return IBGS_EINVAL;
+  }
+  return IBGS_OK;
+}
+
+extern "C" int ibgs_state_layout(int which, size_t count, size_t aux, size_t* offsets, int max,
+                                 size_t* total_bytes) {
+  std::vector<size_t> offs;
+  size_t total = 0;
+  char* base = nullptr;
+  if (which == IBGS_BUF_GEOM) {
+    GeomState g;
+    total = carve_geom(g, base, count);
+    offs = {(size_t)g.rec, (size_t)g.depths, (size_t)g.tiles_touched, (size_t)g.point_offsets, (size_t)g.clamped};
+  } else if (which == IBGS_BUF_IMAGE) {
+    ImageState s;
+    total = carve_image(s, base, count, aux);
+    offs = {(size_t)s.final_T, (size_t)s.n_contrib, (size_t)s.sum_w, (size_t)s.low, (size_t)s.high,
+            (size_t)s.valid_idx, (size_t)s.valid_w, (size_t)s.ranges};
+  } else if (which == IBGS_BUF_BINNING) {
+    BinningState b;
+    total = carve_binning(b, base, count);
+    offs = {(size_t)b.point_list};
+  } else if (which == IBGS_BUF_SCRATCH) {
+    // the (second) forward scratch request: binning temporaries for R=count instances
+    (void)aux;
+    ScratchState sc;
+    total = carve_scratch(sc, base, count, 64);
+    offs = {(size_t)sc.keys_unsorted, (size_t)sc.keys_sorted, (size_t)sc.vals_unsorted, (size_t)sc.sort_temp};
+  } else {
+    ibgs_set_error("unknown buffer id %d", which);
+    return IBGS_EINVAL;
+  }
+  for (int i = 0; i < (int)offs.size() && i < max; i++) offsets[i] = offs[i];
+  if (total_bytes) *total_bytes = total;
+  return (int)offs.size();
+}
+
+extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
+  cudaStream_t s = (cudaStream_t)stream_v;
+  if (!a) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
+  a->tex_generation_out = 0;
+  const int P = a->P;
+  if (P < 0) { ibgs_set_error("P must be >= 0"); return IBGS_EINVAL; }
+  if (P == 0) return 0;  // rasterize_points.cu:101-102: outputs stay zero, rendered = 0
+  const IbgsView& v = a->view;
+  int rc = check_view(v, v.render_geo != 0);
+  if (rc != IBGS_OK) return rc;
+  if (!a->means3D || !a->opacities || !a->radii || !a->alloc) {
+    ibgs_set_error("means3D / opacities / radii / alloc must not be NULL");
+    return IBGS_EINVAL;
+  }
+  if (!a->cov3D_precomp && (!a->scales || !a->rotations)) {
+    ibgs_set_error("provide scales+rotations or cov3D_precomp");
+    return IBGS_EINVAL;
+  }
+  if (!a->colors_precomp && !a->shs && !v.render_depth_only) {
+    ibgs_set_error("provide shs or colors_precomp");
+    return IBGS_EINVAL;
+  }
+  if ((v.render_geo || v.render_depth_only) && !a->all_map) {
+    ibgs_set_error("render_geo / render_depth_only need all_map");
+    return IBGS_EINVAL;
+  }
+  const int W = v.image_width, H = v.image_height;
+  const float focal_y = H / (2.0f * v.tanfovy);  // rasterizer_impl.cu:362-363
+  const float focal_x = W / (2.0f * v.tanfovx);
+  dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
+  const size_t N = (size_t)W * H, T = (size_t)grid.x * grid.y;
+
+  GeomState g;
+  ImageState im;
+  size_t geom_bytes = carve_geom(g, nullptr, (size_t)P);
+  size_t image_bytes = carve_image(im, nullptr, N, T);
+  char* geom_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_GEOM, geom_bytes);
+  char* image_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_IMAGE, image_bytes);
+  if (!geom_base || !image_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  carve_geom(g, geom_base, (size_t)P);
+  carve_image(im, image_base, N, T);
+
+  // textures first: their fill overlaps nothing it depends on and keeps the stream busy
+  TexPair tex = {0, 0};
+  if (v.render_geo) {
+    rc = textures_acquire(W, H, v.nb_src_images, v.src_images, v.src_rendered_depths, s, &tex,
+                          &a->tex_generation_out, 0);
+    if (rc != IBGS_OK) return rc;
+  }
+
+  rc = launch_preprocess(*a, g, focal_x, focal_y, grid, s);
+  if (rc != IBGS_OK) return rc;
+
+  // scan needs a little temp space: take it from a first scratch request sized for the scan only
+  const size_t scan_bytes = align_up(scan_temp_bytes((size_t)P), 256);
+  if (!g_pinned_count) CUDA_TRY(cudaHostAlloc((void**)&g_pinned_count, 64, cudaHostAllocDefault));
+
+  // We do not know R yet; ask for the scan temp now, and for the binning scratch once R is known.
+  char* scan_temp = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, scan_bytes);
+  if (!scan_temp) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  rc = run_scan(g, (size_t)P, scan_temp, scan_bytes, s);
+  if (rc != IBGS_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g_pinned_count, g.point_offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const uint32_t R_u = *(volatile uint32_t*)g_pinned_count;
+  if (R_u > 0x7fffffffu) {
+    // the reference stores this in an int (rasterizer_impl.cu:429) and would overflow
+    ibgs_set_error("num_rendered %u exceeds the int32 limit of the reference layout", R_u);
+    return IBGS_ELIMIT;
+  }
+  const int64_t R = (int64_t)R_u;
+
+  BinningState b;
+  size_t bin_bytes = carve_binning(b, nullptr, (size_t)R);
+  char* bin_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_BINNING, bin_bytes);
+  if (!bin_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  carve_binning(b, bin_base, (size_t)R);
+
+  ScratchState sc;
+  size_t scratch_bytes = carve_scratch(sc, nullptr, (size_t)R, ibgs_sort_bits((int32_t)T));
+  // second scratch request replaces the first (the caller may free the scan temp, stream-ordered)
+  char* scratch_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, scratch_bytes);
+  if (!scratch_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  rc = run_binning(*a, g, im, scratch_base, scratch_bytes, b, R, grid, s);
+  if (rc != IBGS_OK) return rc;
+
+  rc = launch_render_forward(*a, g, im, b, tex, focal_x, focal_y, grid, s);
+  if (rc != IBGS_OK) return rc;
+  return R;
+}
+
+extern "C" int ibgs_backward(IbgsBackwardArgs* a, void* stream_v) {
+  cudaStream_t s = (cudaStream_t)stream_v;
+  if (!a) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
+  const int P = a->P;
+  if (P < 0) { ibgs_set_error("P must be >= 0"); return IBGS_EINVAL; }
+  if (P == 0) return IBGS_OK;
+  const IbgsView& v = a->view;
+  int rc = check_view(v, v.render_geo != 0);
+  if (rc != IBGS_OK) return rc;
+  if (!a->geom_buffer || !a->binning_buffer || !a->image_buffer || !a->alloc || !a->means3D || !a->radii ||
+      !a->dL_dout_color) {
+    ibgs_set_error("state buffers / alloc / means3D / radii / dL_dout_color must not be NULL");
+    return IBGS_EINVAL;
+  }
+  if (v.render_geo && (!a->dL_dout_normal_map || !a->dL_dout_median_intersected_depth ||
+                       !a->dL_dout_warped_image || !a->out_median_intersected_depth || !a->out_warped_image)) {
+    ibgs_set_error("render_geo backward needs the normal/depth/warped cotangents and saved outputs");
+    return IBGS_EINVAL;
+  }
+  if (!a->dL_dmeans3D || !a->dL_dmeans2D || !a->dL_dmeans2D_abs || !a->dL_dcolors || !a->dL_dopacity ||
+      !a->dL_dscales || !a->dL_drotations || !a->dL_dall_map || (a->shs && !a->dL_dsh)) {
+    ibgs_set_error("gradient output pointers must not be NULL");
+    return IBGS_EINVAL;
+  }
+  const int W = v.image_width, H = v.image_height;
+  const float focal_y = H / (2.0f * v.tanfovy);  // rasterizer_impl.cu:578-579
+  const float focal_x = W / (2.0f * v.tanfovx);
+  dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
+  const size_t N = (size_t)W * H, T = (size_t)grid.x * grid.y;
+
+  GeomState g;
+  ImageState im;
+  BinningState b;
+  carve_geom(g, (char*)a->geom_buffer, (size_t)P);
+  carve_image(im, (char*)a->image_buffer, N, T);
+  carve_binning(b, (char*)a->binning_buffer, (size_t)a->R);
+
+  const size_t arena_bytes = (size_t)P * 64;
+  float4* arena = (float4*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, arena_bytes);
+  if (!arena) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  CUDA_TRY(cudaMemsetAsync(arena, 0, arena_bytes, s));
+
+  TexPair tex = {0, 0};
+  if (v.render_geo) {
+    int64_t gen = 0;
+    rc = textures_acquire(W, H, v.nb_src_images, v.src_images, v.src_rendered_depths, s, &tex, &gen,
+                          a->tex_generation);
+    if (rc != IBGS_OK) return rc;
+  }
+  rc = launch_render_backward(*a, g, im, b, tex, focal_x, focal_y, grid, arena, s);
+  if (rc != IBGS_OK) return rc;
+  rc = launch_preprocess_backward(*a, g, arena, focal_x, focal_y, s);
+  return rc;
+}
+
+extern "C" int ibgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                                 const float* projmatrix, uint8_t* present, void* stream) {
+  if (P < 0) { ibgs_set_error("P must be >= 0"); return IBGS_EINVAL; }
+  if (P == 0) return IBGS_OK;
+  if (!means3D || !viewmatrix || !present) { ibgs_set_error("null pointer"); return IBGS_EINVAL; }
+  return launch_mark_visible(P, means3D, viewmatrix, projmatrix, present, (cudaStream_t)stream);
+}

@@ -1,0 +1,151 @@
+// host_api.cu -- host-buffer convenience entry points (ibgs_forward_h, ibgs_dist2_h).
+//
+// What a caller without a device allocator binds (cgo / JNI / ctypes on plain host arrays): every
+// pointer in the argument struct is a HOST pointer; inputs are staged to the device, the device entry
+// point runs on a private stream, outputs are copied back before returning.  State buffers are freed
+// on return, so this path is forward / inference only (reference analogue: render.py's no_grad loop,
+// render.py:297).
+#include "common.cuh"
+#include <vector>
+
+namespace {
+
+struct DevPool {
+  cudaStream_t s = nullptr;
+  std::vector<void*> ptrs;
+  void* get(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaMallocAsync(&p, bytes, s) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    return p;
+  }
+  template <typename T>
+  const T* up(const T* host, size_t count) {
+    if (!host) return nullptr;
+    void* p = get(count * sizeof(T));
+    if (!p) return nullptr;
+    if (cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, s) != cudaSuccess) return nullptr;
+    return (const T*)p;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFreeAsync(p, s);
+    ptrs.clear();
+  }
+};
+
+void* pool_alloc(void* user, int which, size_t bytes) {
+  (void)which;
+  return ((DevPool*)user)->get(bytes);
+}
+
+template <typename T>
+struct Out {
+  T* host;
+  T* dev;
+  size_t count;
+};
+
+}  // namespace
+
+extern "C" int64_t ibgs_forward_h(IbgsForwardArgs* h) {
+  if (!h) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
+  DevPool pool;
+  CUDA_TRY(cudaStreamCreateWithFlags(&pool.s, cudaStreamNonBlocking));
+  const size_t P = (size_t)h->P;
+  const IbgsView& hv = h->view;
+  const size_t N = (size_t)hv.image_width * hv.image_height;
+  const size_t nb = (size_t)hv.nb_src_images;
+  const size_t M = (size_t)hv.sh_coeffs;
+
+  IbgsForwardArgs d = *h;
+  d.view.bg = pool.up(hv.bg, 3);
+  d.view.viewmatrix = pool.up(hv.viewmatrix, 16);
+  d.view.projmatrix = pool.up(hv.projmatrix, 16);
+  d.view.campos = pool.up(hv.campos, 3);
+  d.view.ref_to_src_list = pool.up(hv.ref_to_src_list, nb * 16);
+  d.view.src_cam_pos = pool.up(hv.src_cam_pos, nb * 3);
+  d.view.src_images = pool.up(hv.src_images, nb * 3 * N);
+  d.view.src_rendered_depths = pool.up(hv.src_rendered_depths, nb * N);
+  d.means3D = pool.up(h->means3D, P * 3);
+  d.shs = pool.up(h->shs, P * M * 3);
+  d.colors_precomp = pool.up(h->colors_precomp, P * 3);
+  d.opacities = pool.up(h->opacities, P);
+  d.scales = pool.up(h->scales, P * 3);
+  d.rotations = pool.up(h->rotations, P * 4);
+  d.cov3D_precomp = pool.up(h->cov3D_precomp, P * 6);
+  d.all_map = pool.up(h->all_map, P * 5);
+
+  std::vector<Out<float>> fouts = {{h->out_color, nullptr, 3 * N},
+                                   {h->out_normal_map, nullptr, 3 * N},
+                                   {h->out_median_intersected_depth, nullptr, N},
+                                   {h->out_cam_feat, nullptr, 4 * MAX_SRC * N},
+                                   {h->out_warped_image, nullptr, 3 * MAX_SRC * N},
+                                   {h->out_min_depth_diff, nullptr, N},
+                                   {h->out_camera_ray, nullptr, 3 * N}};
+  for (auto& o : fouts) {
+    o.dev = (float*)pool.get(o.count * sizeof(float));
+    if (!o.dev) { pool.release(); ibgs_set_error("device allocation failed"); return IBGS_EALLOC; }
+    cudaMemsetAsync(o.dev, 0, o.count * sizeof(float), pool.s);
+  }
+  int32_t* radii_d = (int32_t*)pool.get((P ? P : 1) * sizeof(int32_t));
+  int32_t* mask_d = (int32_t*)pool.get(N * sizeof(int32_t));
+  if (!radii_d || !mask_d) { pool.release(); ibgs_set_error("device allocation failed"); return IBGS_EALLOC; }
+  cudaMemsetAsync(radii_d, 0, (P ? P : 1) * sizeof(int32_t), pool.s);
+  cudaMemsetAsync(mask_d, 0, N * sizeof(int32_t), pool.s);
+  d.out_color = fouts[0].dev;
+  d.out_normal_map = fouts[1].dev;
+  d.out_median_intersected_depth = fouts[2].dev;
+  d.out_cam_feat = fouts[3].dev;
+  d.out_warped_image = fouts[4].dev;
+  d.out_min_depth_diff = fouts[5].dev;
+  d.out_camera_ray = fouts[6].dev;
+  d.radii = radii_d;
+  d.out_use_first_src_frame = mask_d;
+  d.alloc = pool_alloc;
+  d.alloc_user = &pool;
+
+  int64_t R = ibgs_forward(&d, pool.s);
+  if (R >= 0) {
+    for (auto& o : fouts)
+      if (o.host) cudaMemcpyAsync(o.host, o.dev, o.count * sizeof(float), cudaMemcpyDeviceToHost, pool.s);
+    if (h->radii) cudaMemcpyAsync(h->radii, radii_d, P * sizeof(int32_t), cudaMemcpyDeviceToHost, pool.s);
+    if (h->out_use_first_src_frame)
+      cudaMemcpyAsync(h->out_use_first_src_frame, mask_d, N * sizeof(int32_t), cudaMemcpyDeviceToHost, pool.s);
+  }
+  pool.release();
+  cudaError_t e = cudaStreamSynchronize(pool.s);
+  cudaStreamDestroy(pool.s);
+  if (R >= 0 && e != cudaSuccess) {
+    ibgs_set_error("ibgs_forward_h: %s", cudaGetErrorString(e));
+    return IBGS_ECUDA;
+  }
+  return R;
+}
+
+extern "C" int ibgs_dist2_h(int32_t P, const float* points_host, float* mean_dists_host) {
+  if (P < 0) { ibgs_set_error("P must be >= 0"); return IBGS_EINVAL; }
+  if (P == 0) return IBGS_OK;
+  if (!points_host || !mean_dists_host) { ibgs_set_error("null pointer"); return IBGS_EINVAL; }
+  DevPool pool;
+  CUDA_TRY(cudaStreamCreateWithFlags(&pool.s, cudaStreamNonBlocking));
+  const float* pts = pool.up(points_host, (size_t)P * 3);
+  float* out = (float*)pool.get((size_t)P * sizeof(float));
+  size_t sb = ibgs_dist2_scratch_bytes(P);
+  void* scratch = pool.get(sb);
+  int rc = IBGS_EALLOC;
+  if (pts && out && scratch) {
+    rc = ibgs_dist2(P, pts, out, scratch, sb, pool.s);
+    if (rc == IBGS_OK) cudaMemcpyAsync(mean_dists_host, out, (size_t)P * sizeof(float), cudaMemcpyDeviceToHost, pool.s);
+  } else {
+    ibgs_set_error("device allocation failed");
+  }
+  pool.release();
+  cudaError_t e = cudaStreamSynchronize(pool.s);
+  cudaStreamDestroy(pool.s);
+  if (rc == IBGS_OK && e != cudaSuccess) {
+    ibgs_set_error("ibgs_dist2_h: %s", cudaGetErrorString(e));
+    return IBGS_ECUDA;
+  }
+  return rc;
+}

@@ -1,0 +1,142 @@
+// textures.cu -- persistent layered textures for the source-view colour / depth taps.
+//
+// Reference behaviour: createLayeredTextures / destroyLayeredTextures (rasterizer_impl.cu:58-148):
+// per call cudaMalloc3DArray x2 + cudaMalloc + packRGBA kernel + cudaDeviceSynchronize + two
+// cudaMemcpy3D + two texture objects, torn down again with cudaFree/cudaFreeArray -- in EVERY forward
+// and EVERY backward (:366,512,582,638).  Sampling is cudaFilterModeLinear / clamp / unnormalised /
+// element-type float4 (colour, alpha=1) and float (depth) (:117-130).
+//
+// Here the arrays and texture objects are created once per (device, stream, W, H, layers) and
+// refilled by one kernel that writes the planar source tensors straight into the arrays through
+// surface objects -- no staging buffer, no host synchronisation, no allocation on the hot path.
+// Sampling goes through the same hardware filter, so the 8-bit-weight bilinear taps are identical.
+// A fill gets a generation number; the backward pass of the same view reuses the fill if its
+// generation is still current.
+#include "common.cuh"
+#include <vector>
+#include <mutex>
+
+namespace {
+
+struct TexEntry {
+  int device, W, H, layers;
+  cudaStream_t stream;
+  cudaArray_t color_array = nullptr, depth_array = nullptr;
+  cudaSurfaceObject_t color_surf = 0, depth_surf = 0;
+  cudaTextureObject_t color_tex = 0, depth_tex = 0;
+  int64_t generation = 0;
+  const float* last_images = nullptr;
+  const float* last_depths = nullptr;
+};
+
+std::vector<TexEntry> g_pool;
+std::mutex g_mu;
+int64_t g_generation = 0;
+
+// one thread per (x, y, layer); reads planar [layer][3][H][W] / [layer][1][H][W]
+__global__ void fill_layers_kernel(const float* __restrict__ images, const float* __restrict__ depths, int W,
+                                   int H, int layers, cudaSurfaceObject_t color, cudaSurfaceObject_t depth) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int l = blockIdx.z;
+  if (x >= W) return;
+  const size_t plane = (size_t)W * H;
+  const size_t pix = (size_t)y * W + x;
+  const float* im = images + (size_t)l * 3 * plane + pix;
+  float4 rgba = make_float4(im[0], im[plane], im[2 * plane], 1.0f);  // packRGBA, rasterizer_impl.cu:52-55
+  surf2DLayeredwrite(rgba, color, x * (int)sizeof(float4), y, l);
+  surf2DLayeredwrite(depths[(size_t)l * plane + pix], depth, x * (int)sizeof(float), y, l);
+}
+
+int create_entry(TexEntry& e) {
+  cudaChannelFormatDesc cC = cudaCreateChannelDesc<float4>();
+  cudaChannelFormatDesc cD = cudaCreateChannelDesc<float>();
+  cudaExtent ext = make_cudaExtent(e.W, e.H, e.layers);
+  CUDA_TRY(cudaMalloc3DArray(&e.color_array, &cC, ext, cudaArrayLayered | cudaArraySurfaceLoadStore));
+  CUDA_TRY(cudaMalloc3DArray(&e.depth_array, &cD, ext, cudaArrayLayered | cudaArraySurfaceLoadStore));
+  cudaResourceDesc res = {};
+  res.resType = cudaResourceTypeArray;
+  cudaTextureDesc td = {};
+  td.addressMode[0] = cudaAddressModeClamp;
+  td.addressMode[1] = cudaAddressModeClamp;
+  td.filterMode = cudaFilterModeLinear;
+  td.readMode = cudaReadModeElementType;
+  td.normalizedCoords = 0;
+  res.res.array.array = e.color_array;
+  CUDA_TRY(cudaCreateTextureObject(&e.color_tex, &res, &td, nullptr));
+  CUDA_TRY(cudaCreateSurfaceObject(&e.color_surf, &res));
+  res.res.array.array = e.depth_array;
+  CUDA_TRY(cudaCreateTextureObject(&e.depth_tex, &res, &td, nullptr));
+  CUDA_TRY(cudaCreateSurfaceObject(&e.depth_surf, &res));
+  return IBGS_OK;
+}
+
+void destroy_entry(TexEntry& e) {
+  if (e.color_tex) cudaDestroyTextureObject(e.color_tex);
+  if (e.depth_tex) cudaDestroyTextureObject(e.depth_tex);
+  if (e.color_surf) cudaDestroySurfaceObject(e.color_surf);
+  if (e.depth_surf) cudaDestroySurfaceObject(e.depth_surf);
+  if (e.color_array) cudaFreeArray(e.color_array);
+  if (e.depth_array) cudaFreeArray(e.depth_array);
+  e = TexEntry();
+}
+
+}  // namespace
+
+int textures_acquire(int W, int H, int layers, const float* src_images, const float* src_depths,
+                     cudaStream_t s, TexPair* out, int64_t* generation, int64_t reuse_generation) {
+  out->color = 0;
+  out->depth = 0;
+  if (generation) *generation = 0;
+  if (layers <= 0) return IBGS_OK;  // reference returns empty textures, rasterizer_impl.cu:75-76
+  if (src_images == nullptr || src_depths == nullptr) {
+    ibgs_set_error("src_images / src_rendered_depths must be given when nb_src_images > 0");
+    return IBGS_EINVAL;
+  }
+  std::lock_guard<std::mutex> lock(g_mu);
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  TexEntry* e = nullptr;
+  for (auto& c : g_pool)
+    if (c.device == dev && c.stream == s && c.W == W && c.H == H && c.layers == layers) e = &c;
+  if (!e) {
+    // keep the pool small: drop entries of this (device, stream) with another shape
+    for (size_t i = 0; i < g_pool.size();) {
+      if (g_pool[i].device == dev && g_pool[i].stream == s) {
+        CUDA_TRY(cudaStreamSynchronize(s));
+        destroy_entry(g_pool[i]);
+        g_pool.erase(g_pool.begin() + i);
+      } else {
+        i++;
+      }
+    }
+    TexEntry ne;
+    ne.device = dev; ne.W = W; ne.H = H; ne.layers = layers; ne.stream = s;
+    int rc = create_entry(ne);
+    if (rc != IBGS_OK) { destroy_entry(ne); return rc; }
+    g_pool.push_back(ne);
+    e = &g_pool.back();
+  }
+  const bool reuse = reuse_generation != 0 && reuse_generation == e->generation &&
+                     e->last_images == src_images && e->last_depths == src_depths;
+  if (!reuse) {
+    dim3 block(128, 1, 1);
+    dim3 grid((W + 127) / 128, H, layers);
+    fill_layers_kernel<<<grid, block, 0, s>>>(src_images, src_depths, W, H, layers, e->color_surf,
+                                              e->depth_surf);
+    KERNEL_CHECK(0, s);
+    e->generation = ++g_generation;
+    e->last_images = src_images;
+    e->last_depths = src_depths;
+  }
+  out->color = e->color_tex;
+  out->depth = e->depth_tex;
+  if (generation) *generation = e->generation;
+  return IBGS_OK;
+}
+
+void textures_release_all() {
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (auto& e : g_pool) destroy_entry(e);
+  g_pool.clear();
+}

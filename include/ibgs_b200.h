@@ -1,0 +1,186 @@
+/*
+ * ibgs_b200.h -- C ABI of the B200-native IBGS planar Gaussian rasterizer.
+ *
+ * This is the drop-in boundary for ONE path of HoangChuongNguyen/ibgs: what the reference
+ * binds through pybind11 in submodules/diff-plane-rasterization/ext.cpp:15-19
+ * (rasterize_gaussians / rasterize_gaussians_backward / mark_visible) and
+ * submodules/simple-knn/ext.cpp:15-17 (distCUDA2).  Plain pointers and sizes only; no torch
+ * types.  All data pointers are DEVICE pointers on the current CUDA device unless a `_h`
+ * entry point says otherwise; `stream` is a cudaStream_t passed as void* (NULL = legacy
+ * default stream, which is what the reference always uses: rasterizer_impl.cu launches
+ * `<<<grid,block>>>` without a stream).
+ *
+ * Every entry point returns >= 0 on success and a negative IBGS_E* code on failure;
+ * ibgs_last_error() returns a human-readable message for the calling thread.
+ */
+#ifndef IBGS_B200_H_INCLUDED
+#define IBGS_B200_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBGS_ABI_VERSION 1
+
+/* Compile-time constants of the reference (cuda_rasterizer/config.h:15-19, auxiliary.h:21-23). */
+#define IBGS_NUM_CHANNELS 3
+#define IBGS_NUM_PLANE_PARAMS 5
+#define IBGS_TILE 16
+#define IBGS_MAX_BUFFER_LENGTH 8
+#define IBGS_MAX_SRC 5
+
+enum {
+  IBGS_OK = 0,
+  IBGS_EINVAL = -1,  /* bad argument (shape / null / range) -- reference: rasterize_points.cu:69-71 */
+  IBGS_ECUDA = -2,   /* CUDA runtime error (message has cudaGetErrorString) */
+  IBGS_EALLOC = -3,  /* allocator callback returned NULL */
+  IBGS_ELIMIT = -4   /* num_rendered would exceed the reference's int32 limit (rasterizer_impl.cu:429) */
+};
+
+/* Scratch/state buffers.  The reference hands Rasterizer::forward three std::function<char*(size_t)>
+ * resizers (rasterize_points.cu:29-35,94-99; rasterizer_impl.cu:321-323); this is the C spelling:
+ * the library calls `alloc(user, which, bytes)` and gets device memory owned by the caller.
+ * GEOM / BINNING / IMAGE must stay alive until the matching ibgs_backward; SCRATCH may be released
+ * (stream-ordered) as soon as ibgs_forward returns. */
+enum { IBGS_BUF_GEOM = 0, IBGS_BUF_BINNING = 1, IBGS_BUF_IMAGE = 2, IBGS_BUF_SCRATCH = 3 };
+typedef void* (*ibgs_alloc_fn)(void* user, int which, size_t bytes);
+
+/* View / mode parameters shared by forward and backward
+ * (reference: GaussianRasterizationSettings, diff_plane_rasterization/__init__.py:252-276). */
+typedef struct IbgsView {
+  int32_t image_height, image_width;
+  float tanfovx, tanfovy;
+  float scale_modifier;
+  int32_t sh_degree;          /* active degree D */
+  int32_t sh_coeffs;          /* M = coefficients per channel in `shs` (0 when shs absent) */
+  int32_t nb_src_images;      /* <= IBGS_MAX_SRC */
+  int32_t buffer_length;      /* 1..IBGS_MAX_BUFFER_LENGTH */
+  float depth_error_threshold;
+  int32_t prefiltered, render_geo, render_depth_only, debug;
+  const float* bg;            /* [3] */
+  const float* viewmatrix;    /* [16], torch world_view_transform memory (= column-major W2C) */
+  const float* projmatrix;    /* [16] */
+  const float* campos;        /* [3] */
+  const float* ref_to_src_list;     /* [nb_src,16] row-major */
+  const float* src_cam_pos;         /* [nb_src,3] */
+  const float* src_images;          /* [nb_src,3,H,W] planar */
+  const float* src_rendered_depths; /* [nb_src,1,H,W] */
+} IbgsView;
+
+/* Forward.  Replaces CudaRasterizer::Rasterizer::forward (rasterizer_impl.cu:320-515) as called by
+ * RasterizeGaussiansCUDA (rasterize_points.cu:37-160).  NULL pointer == "absent", as in the
+ * reference (forward.cu:244,280).  Outputs must be pre-zeroed by the caller exactly like the
+ * binding's torch::full(...,0) (rasterize_points.cu:80-90). */
+typedef struct IbgsForwardArgs {
+  int32_t P;
+  IbgsView view;
+  const float* means3D;        /* [P,3] */
+  const float* shs;            /* [P,M,3] or NULL */
+  const float* colors_precomp; /* [P,3] or NULL */
+  const float* opacities;      /* [P] */
+  const float* scales;         /* [P,3] or NULL */
+  const float* rotations;      /* [P,4] or NULL */
+  const float* cov3D_precomp;  /* [P,6] or NULL */
+  const float* all_map;        /* [P,5] or NULL (required for render_geo / render_depth_only) */
+  /* outputs (CHW planar, float32 unless noted) */
+  float* out_color;                     /* [3,H,W] */
+  int32_t* radii;                       /* [P] */
+  float* out_normal_map;                /* [3,H,W] */
+  float* out_median_intersected_depth;  /* [1,H,W] */
+  float* out_cam_feat;                  /* [4*5,H,W] */
+  float* out_warped_image;              /* [3*5,H,W] */
+  float* out_min_depth_diff;            /* [1,H,W] */
+  float* out_camera_ray;                /* [3,H,W] */
+  int32_t* out_use_first_src_frame;     /* [1,H,W] */
+  ibgs_alloc_fn alloc;
+  void* alloc_user;
+  int64_t tex_generation_out;  /* written by the library: id of the texture fill, see backward */
+} IbgsForwardArgs;
+
+/* returns num_rendered (tile instances R) */
+int64_t ibgs_forward(IbgsForwardArgs* args, void* stream);
+
+/* Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:519-666) as called
+ * by RasterizeGaussiansBackwardCUDA (rasterize_points.cu:162-271).  Every dL_* output is fully
+ * written (no pre-zeroing needed), except that rows of Gaussians with radii==0 are written as 0. */
+typedef struct IbgsBackwardArgs {
+  int32_t P;
+  int64_t R;
+  IbgsView view;
+  const float* means3D;
+  const float* shs;
+  const float* colors_precomp;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* all_map;
+  const int32_t* radii;
+  /* saved forward outputs */
+  const float* out_median_intersected_depth;
+  const float* out_warped_image;
+  /* state buffers from the forward allocator */
+  const void* geom_buffer;
+  const void* binning_buffer;
+  const void* image_buffer;
+  int64_t tex_generation;      /* from forward; textures are refilled if it is stale */
+  /* cotangents; only these four are consumed (rasterize_points.cu:205-211) */
+  const float* dL_dout_color;                     /* [3,H,W] */
+  const float* dL_dout_normal_map;                /* [3,H,W] */
+  const float* dL_dout_median_intersected_depth;  /* [1,H,W] */
+  const float* dL_dout_warped_image;              /* [15,H,W] */
+  /* gradients */
+  float* dL_dmeans3D;     /* [P,3] */
+  float* dL_dmeans2D;     /* [P,3] (z column = 0) */
+  float* dL_dmeans2D_abs; /* [P,3] */
+  float* dL_dcolors;      /* [P,3] */
+  float* dL_dopacity;     /* [P,1] */
+  float* dL_dcov3D;       /* [P,6] */
+  float* dL_dsh;          /* [P,M,3] or NULL */
+  float* dL_dscales;      /* [P,3] */
+  float* dL_drotations;   /* [P,4] */
+  float* dL_dall_map;     /* [P,5] */
+  ibgs_alloc_fn alloc;    /* SCRATCH only (per-Gaussian accumulation arena, 64 B/Gaussian) */
+  void* alloc_user;
+} IbgsBackwardArgs;
+
+int ibgs_backward(IbgsBackwardArgs* args, void* stream);
+
+/* markVisible (rasterizer_impl.cu:258-270, kernel :171-183): present[i] = view-space z > 0.2 */
+int ibgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, uint8_t* present, void* stream);
+
+/* simple-knn distCUDA2 (simple_knn.cu:185-221, spatial.cu:15-26): mean squared distance to the three
+ * nearest neighbours.  `scratch` is device memory of at least ibgs_dist2_scratch_bytes(P). */
+size_t ibgs_dist2_scratch_bytes(int32_t P);
+int ibgs_dist2(int32_t P, const float* points, float* mean_dists, void* scratch, size_t scratch_bytes,
+               void* stream);
+
+/* Host-buffer convenience entry points (what a non-torch caller binds; used by bench.py's e2e arm):
+ * identical semantics, but every pointer in the structs is a HOST pointer; the library stages
+ * through its own device arena (cudaMallocAsync) and copies results back before returning. */
+int64_t ibgs_forward_h(IbgsForwardArgs* host_args);
+int ibgs_dist2_h(int32_t P, const float* points_host, float* mean_dists_host);
+
+/* State-layout introspection (tests decode the buffers with this, mirroring how the reference's
+ * GeometryState/ImageState/BinningState::fromChunk carve theirs, rasterizer_impl.cu:272-316).
+ * Writes up to `max` byte offsets; returns the number of arrays in the buffer. `count` is P for GEOM,
+ * R for BINNING/SCRATCH, W*H for IMAGE (aux = number of tiles for IMAGE, unused otherwise). */
+int ibgs_state_layout(int which, size_t count, size_t aux, size_t* offsets, int max, size_t* total_bytes);
+
+/* Tile-instance sort-key width: 32 + getHigherMsb(tiles) (rasterizer_impl.cu:152-167,449). */
+int ibgs_sort_bits(int32_t num_tiles);
+
+const char* ibgs_last_error(void);
+int ibgs_abi_version(void);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches counter). */
+int64_t ibgs_launch_count(void);
+/* Releases cached textures / arenas. */
+void ibgs_release_cached(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBGS_B200_H_INCLUDED */

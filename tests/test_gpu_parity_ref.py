@@ -1,0 +1,137 @@
+"""GPU parity: this implementation (through its public API -> C ABI) vs the UNMODIFIED reference CUDA
+extension (oracle/_ref, built from /root/reference by oracle/build_ref.py) on identical synthetic scenes.
+
+Gates: radii / tiles_touched / num_rendered / unsorted+sorted keys / point_list /
+ranges / n_contrib bit-exact; float outputs <= 1e-4 max-abs; gradients <= 1e-3 relative L2.
+"""
+import pytest
+import torch
+
+from ibgs_b200 import synthetic as S
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dpr():
+    import ibgs_b200.diff_plane_rasterization as d
+    return d
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import ref_ext
+    if not ref_ext.available("dpr"):
+        pytest.skip("oracle/_ref/dpr/ref_dpr_C.so not built")
+    ref_ext.load("dpr")
+    return ref_ext
+
+
+def _scene(dpr, name, **kw):
+    sc = U.scene_to_device(S.make_scene(name, **kw))
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    return sc
+
+
+def _check_binning(ours, rg, rb, ri, R, T):
+    assert torch.equal(ours["tiles_touched"], rg["tiles_touched"])
+    assert torch.equal(ours["point_offsets"], rg["point_offsets"])
+    vis = rg["tiles_touched"] > 0
+    assert torch.equal(ours["depths"][vis].view(torch.int32), rg["depths"][vis].view(torch.int32))
+    assert torch.equal(ours["means2D"][vis].view(torch.int32), rg["means2D"][vis].view(torch.int32))
+    assert torch.equal(ours["conic_opacity"][vis].view(torch.int32), rg["conic_opacity"][vis].view(torch.int32))
+    assert torch.equal(ours["keys_unsorted"], rb["keys_unsorted"])
+    assert torch.equal(ours["point_list_unsorted"], rb["point_list_unsorted"])
+    assert torch.equal(ours["keys"], rb["keys"])
+    assert torch.equal(ours["point_list"], rb["point_list"])
+    assert torch.equal(ours["ranges"], ri["ranges"][:T])
+
+
+@pytest.mark.parametrize("name,kw", [("tiny", {}), ("cfg1", {}), ("cfg1", {"identity_pose": True, "seed": 3})])
+def test_geo_forward_backward_vs_reference(dpr, ref, name, kw):
+    sc = _scene(dpr, name, **kw)
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    outs, grads, state = U.ours_forward_backward(dpr, sc, cot, render_geo=True)
+    fw = ref.forward(sc, render_geo=True)
+    P, H, W = sc["P"], sc["H"], sc["W"]
+    N = H * W
+    T = ((W + 15) // 16) * ((H + 15) // 16)
+    R = fw["num_rendered"]
+    assert state["num_rendered"] == R
+    assert torch.equal(outs["radii"], fw["radii"])
+    ours = U.decode_ours(state)
+    rg, ri, rb = ref.decode_geom(fw["geom"], P), ref.decode_image(fw["img"], N), ref.decode_binning(fw["binning"], R)
+    _check_binning(ours, rg, rb, ri, R, T)
+    # per-pixel state
+    assert torch.equal(ours["n_contrib"], ri["n_contrib"])
+    assert torch.equal(ours["final_T"].view(torch.int32), ri["final_T"].view(torch.int32))
+    assert torch.equal(ours["low"], ri["low"]) and torch.equal(ours["high"], ri["high"])
+    assert torch.equal(outs["mask"], fw["mask"])
+    for k in ("color", "normal", "depth", "cam_feat", "warped", "min_depth_diff", "camera_ray"):
+        err = (outs[k] - fw[k]).abs().max().item()
+        assert err <= 1e-4, f"{k}: max-abs {err}"
+    rgrads = ref.backward(sc, fw, cot, render_geo=True)
+    for k in U.GRAD_NAMES:
+        e = U.rel_l2(grads[k], rgrads[k].view_as(grads[k]))
+        assert e <= 1e-3, f"grad {k}: rel-L2 {e}"
+
+
+def test_color_only_vs_reference(dpr, ref):
+    sc = _scene(dpr, "cfg1")
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    outs, grads, state = U.ours_forward_backward(dpr, sc, cot, render_geo=False)
+    sc1 = dict(sc)
+    H, W = sc["H"], sc["W"]
+    sc1.update(nb_src=1, ref_to_src_list=torch.zeros((1, 16), device="cuda"),
+               src_images=torch.zeros((1, 3, H * W), device="cuda"),
+               src_rendered_depths=torch.zeros((1, 1, H * W), device="cuda"),
+               src_cam_pos=torch.zeros((1, 3), device="cuda"))
+    fw = ref.forward(sc1, render_geo=False)
+    assert state["num_rendered"] == fw["num_rendered"]
+    assert torch.equal(outs["radii"], fw["radii"])
+    assert (outs["color"] - fw["color"]).abs().max().item() <= 1e-4
+    for k in ("normal", "depth", "cam_feat", "warped", "min_depth_diff", "camera_ray"):
+        assert outs[k].abs().max().item() == 0.0  # untouched zero fill, as in the reference
+    rgrads = ref.backward(sc1, fw, cot, render_geo=False)
+    for k in ("means3D", "means2D", "means2D_abs", "sh", "opacities", "scales", "rotations"):
+        e = U.rel_l2(grads[k], rgrads[k].view_as(grads[k]))
+        assert e <= 1e-3, f"grad {k}: rel-L2 {e}"
+
+
+@pytest.mark.parametrize("bl", [1, 2, 3, 4, 5, 8])
+def test_depth_only_vs_reference(dpr, ref, bl):
+    sc = _scene(dpr, "cfg1")
+    outs, _, state = U.ours_forward_backward(dpr, sc, None, render_geo=False, render_depth_only=True,
+                                             buffer_length=bl)
+    fw = ref.forward(sc, render_geo=False, render_depth_only=True, buffer_length=bl)
+    assert state["num_rendered"] == fw["num_rendered"]
+    err = (outs["depth"] - fw["depth"]).abs().max().item()
+    assert err <= 1e-4, f"depth-only BL={bl}: {err}"
+    assert outs["color"].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("bl", [1, 2, 3, 5, 8])
+def test_geo_buffer_lengths_vs_reference(dpr, ref, bl):
+    sc = _scene(dpr, "tiny")
+    outs, _, state = U.ours_forward_backward(dpr, sc, None, render_geo=True, buffer_length=bl,
+                                             depth_error_threshold=0.05)
+    fw = ref.forward(sc, render_geo=True, buffer_length=bl, depth_error_threshold=0.05)
+    for k in ("color", "normal", "depth", "cam_feat", "warped", "min_depth_diff", "camera_ray"):
+        err = (outs[k] - fw[k]).abs().max().item()
+        assert err <= 1e-4, f"BL={bl} {k}: max-abs {err}"
+    assert torch.equal(outs["mask"], fw["mask"])
+
+
+def test_mark_visible_and_knn_vs_reference(dpr, ref):
+    sc = _scene(dpr, "cfg1")
+    rs = U.make_settings(dpr, sc)
+    vis = dpr.GaussianRasterizer(rs).markVisible(sc["means3D"])
+    rvis = ref.load("dpr").mark_visible(sc["means3D"], sc["viewmatrix"], sc["projmatrix"])
+    assert torch.equal(vis, rvis)
+    if ref.available("knn"):
+        from ibgs_b200.simple_knn._C import distCUDA2
+        for n in (1, 5, 1000, 10_000, 200_003):
+            pts = torch.randn((n, 3), generator=torch.Generator().manual_seed(n)).cuda() * 3.0
+            a, b = distCUDA2(pts), ref.dist2(pts)
+            assert torch.allclose(a, b, rtol=1e-6, atol=0), f"knn n={n}: {(a - b).abs().max().item()}"

@@ -1,0 +1,118 @@
+"""Quick A/B timing of this implementation vs the reference extension on one synthetic scene (dev tool).
+usage: python tools/quick_ab.py cfg2 [--iters 10] [--no-ref]"""
+import argparse
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ibgs_b200 import synthetic as S  # noqa: E402
+import ibgs_b200.diff_plane_rasterization as dpr  # noqa: E402
+from tests import util as U  # noqa: E402
+
+
+def timed(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("name")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--no-ref", action="store_true")
+    ap.add_argument("--geo", type=int, default=1)
+    a = ap.parse_args()
+    t0 = time.time()
+    sc = U.scene_to_device(S.make_scene(a.name))
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    print(f"scene {a.name}: P={sc['P']} {sc['W']}x{sc['H']} built in {time.time()-t0:.1f}s", flush=True)
+    geo = bool(a.geo)
+    rs = U.make_settings(dpr, sc, render_geo=geo)
+    leaf = {k: sc[k].detach().clone().requires_grad_(True)
+            for k in ("means3D", "shs", "opacities", "scales", "rotations", "all_map")}
+    m2d = torch.zeros_like(sc["means3D"], requires_grad=True)
+    m2a = torch.zeros_like(sc["means3D"], requires_grad=True)
+    rast = dpr.GaussianRasterizer(rs)
+    state = {}
+
+    def ours_fwd():
+        state["res"] = rast(means3D=leaf["means3D"], means2D=m2d, means2D_abs=m2a, opacities=leaf["opacities"],
+                            shs=leaf["shs"], scales=leaf["scales"], rotations=leaf["rotations"],
+                            all_map=leaf["all_map"] if geo else None)
+
+    def ours_bwd():
+        r = state["res"]
+        outs = [r[0]] + ([r[2], r[3], r[5]] if geo else [])
+        gs = [cot["color"]] + ([cot["normal"], cot["depth"], cot["warped"]] if geo else [])
+        torch.autograd.backward(outs, gs)
+
+    def ours_both():
+        ours_fwd()
+        ours_bwd()
+
+    f = timed(ours_fwd, a.iters)
+    ours_fwd()
+    torch.cuda.synchronize()
+    # backward alone: re-run forward untimed each iteration
+    tb = []
+    for _ in range(a.iters):
+        ours_fwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); ours_bwd(); e1.record(); torch.cuda.synchronize()
+        tb.append(e0.elapsed_time(e1))
+    tb.sort()
+    both = timed(ours_both, a.iters)
+    U.ours_forward_backward  # noqa
+    dpr.KEEP_STATE = True
+    ours_fwd()
+    dpr.KEEP_STATE = False
+    R = dpr.LAST_STATE["num_rendered"]
+    print(f"OURS  {a.name} geo={geo}: R={R} fwd {f:.3f} ms  bwd {tb[len(tb)//2]:.3f} ms  fwd+bwd {both:.3f} ms", flush=True)
+
+    if not a.no_ref:
+        from oracle import ref_ext
+        sc1 = sc
+        if not geo:
+            H, W = sc["H"], sc["W"]
+            sc1 = dict(sc)
+            sc1.update(nb_src=1, ref_to_src_list=torch.zeros((1, 16), device="cuda"),
+                       src_images=torch.zeros((1, 3, H * W), device="cuda"),
+                       src_rendered_depths=torch.zeros((1, 1, H * W), device="cuda"),
+                       src_cam_pos=torch.zeros((1, 3), device="cuda"))
+        st = {}
+
+        def ref_fwd():
+            st["fw"] = ref_ext.forward(sc1, render_geo=geo)
+
+        def ref_bwd():
+            ref_ext.backward(sc1, st["fw"], cot, render_geo=geo)
+
+        def ref_both():
+            ref_fwd(); ref_bwd()
+
+        rf = timed(ref_fwd, a.iters)
+        ref_fwd(); torch.cuda.synchronize()
+        rb = timed(ref_bwd, a.iters)
+        rboth = timed(ref_both, a.iters)
+        print(f"REF   {a.name} geo={geo}: R={st['fw']['num_rendered']} fwd {rf:.3f} ms  bwd {rb:.3f} ms  fwd+bwd {rboth:.3f} ms"
+              f"   speedup fwd+bwd x{rboth/both:.2f}", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,7 @@ def make_camera(w2c, W, H, fovx_deg=60.0):
 
 def all_map_for_view(means3D, normals_world, viewmatrix, campos):
     """gaussian_renderer/__init__.py:304-315 with learnt_normal=True, offset=0 (float32 torch ops)."""
+    viewmatrix, campos = viewmatrix.to(means3D.device), campos.to(means3D.device)
     n = normals_world / torch.norm(normals_world, dim=1, keepdim=True)
     to_cam = campos.unsqueeze(0) - means3D
     neg = (n * to_cam).sum(-1) < 0.0
@@ -77,7 +78,7 @@ def all_map_for_view(means3D, normals_world, viewmatrix, campos):
     local_n = n @ viewmatrix[:3, :3]
     gdist = -(n * means3D).sum(-1)
     ldist = (gdist - torch.sum(local_n * viewmatrix[[3], :3], dim=1)).abs()
-    am = torch.zeros((means3D.shape[0], 5), dtype=torch.float32)
+    am = torch.zeros((means3D.shape[0], 5), dtype=torch.float32, device=means3D.device)
     am[:, :3] = local_n
     am[:, 3] = 1.0
     am[:, 4] = ldist

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from ibgs_b200 import synthetic as S
-from tests import util as U
+import ibgs_testutil as U
 
 pytestmark = pytest.mark.gpu
 

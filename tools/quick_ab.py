@@ -10,7 +10,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ibgs_b200 import synthetic as S  # noqa: E402
 import ibgs_b200.diff_plane_rasterization as dpr  # noqa: E402
-from tests import util as U  # noqa: E402
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import ibgs_testutil as U  # noqa: E402
 
 
 def timed(fn, iters, warm=3):

@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the IBGS planar Gaussian rasterizer hot path.
+
+Metric (BASELINE.json): forward+backward rasterization of 3M Gaussians at 1920x1080 (render_geo mode: colour +
+normal + median plane depth + 4 warped source views), reported as whole-job views/s (ms/view = 1000 * n_gpus *
+views_per_step / (value)).  A "step" = every rank renders `views_per_step` different camera views
+(forward + backward, gradients accumulated into one flat per-Gaussian arena) and, for N > 1, one NCCL
+all-reduce of that arena.  Weak scaling: per-GPU work is fixed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config cfg3_1080p]
+
+  value   inputs resident in HBM when the timed region starts
+  e2e     same step through the public API, but every view's source images / depths / camera block start in
+          PINNED HOST memory and are copied H2D inside the timed region (prefetched on a copy stream), and a
+          scalar loss is read back D2H every step
+`--impl reference` times the UNMODIFIED reference CUDA extension (oracle/_ref, built from /root/reference by
+oracle/build_ref.py) on the same scene, metric and step; under torchrun only rank 0 runs it (the reference is
+single-GPU: train.py:277-292).  If the extension is not available the CPU oracle port is timed instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "fwd+bwd rasterize views/s @1080p, 3M Gaussians (render_geo, 4 src views)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg3_1080p")
+    ap.add_argument("--views-per-step", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+def start_clock_sampler(dev_index):
+    path = tempfile.mktemp(suffix=".csv")
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    try:
+        f = open(path, "w")
+        p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                              "-i", str(dev_index)], stdout=f, stderr=subprocess.DEVNULL)
+        return p, path
+    except Exception:
+        return None, path
+
+
+def stop_clock_sampler(p, path):
+    out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+    if p is None:
+        return out
+    p.terminate()
+    try:
+        p.wait(timeout=5)
+    except Exception:
+        p.kill()
+    try:
+        rows = [r.strip().split(",") for r in open(path) if r.strip()]
+        sm = [float(r[1]) for r in rows if len(r) >= 9]
+        if sm:
+            out["samples"] = len(sm)
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(rows[0][2])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for i, n in enumerate(names):
+                if any(r[5 + i].strip().lower().startswith("active") for r in rows if len(r) >= 9):
+                    out["reasons"].append(n)
+        os.unlink(path)
+    except Exception:
+        pass
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+class Workload:
+    """Scene + per-rank view batch.  Everything derived (all_map per view, source depths) is prepared
+    untimed, as the training loop would have it resident before calling the rasterizer."""
+
+    def __init__(self, args, rank, world, device, impl_mod):
+        from ibgs_b200 import synthetic as S
+        import ibgs_testutil as U
+        self.S, self.U = S, U
+        self.device = device
+        sc_cpu = S.make_scene(args.config)
+        self.P, self.W, self.H = sc_cpu["P"], sc_cpu["W"], sc_cpu["H"]
+        self.sc = U.scene_to_device(sc_cpu, device)
+        import ibgs_b200.diff_plane_rasterization as dpr
+        self.dpr = dpr
+        self.sc["src_rendered_depths"] = U.render_src_depths(dpr, self.sc)
+        g = torch.Generator().manual_seed(7)
+        self.cot = {k: v.to(device) for k, v in S.cotangents(sc_cpu).items()}
+        # view batch of this rank: the reference view perturbed by a small rigid motion (seeded per global view id)
+        self.views = []
+        V = args.views_per_step
+        w2c = sc_cpu["w2c"].double().numpy()
+        for i in range(V):
+            gid = rank * V + i
+            rng = np.random.default_rng(1000 + gid)
+            D = S._rigid(S._rot_axis_angle(rng.normal(size=3), np.radians(rng.uniform(0.0, 2.0))),
+                         rng.uniform(-0.1, 0.1, 3)) if gid > 0 else np.eye(4)
+            w2v = D @ w2c
+            cam = S.make_camera(w2v, self.W, self.H)
+            cam = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in cam.items()}
+            cam["all_map"] = S.all_map_for_view(self.sc["means3D"], self.sc["normals_world"], cam["viewmatrix"],
+                                                cam["campos"]).contiguous()
+            r2s = torch.stack([torch.from_numpy(np.float32(m.numpy().astype(np.float64) @ np.linalg.inv(w2v)))
+                               for m in sc_cpu["src_w2c"]]).to(device).contiguous()
+            cam["ref_to_src_list"] = r2s
+            self.views.append(cam)
+        del g
+
+    def scene_for(self, cam, src_images=None, src_depths=None):
+        sc = dict(self.sc)
+        sc.update({k: cam[k] for k in ("viewmatrix", "projmatrix", "campos", "tanfovx", "tanfovy", "all_map",
+                                       "ref_to_src_list")})
+        if src_images is not None:
+            sc["src_images"], sc["src_rendered_depths"] = src_images, src_depths
+        return sc
+
+
+class OursRunner:
+    name = "b200"
+
+    def __init__(self, wl):
+        from ibgs_b200 import parallel as PL
+        from ibgs_b200 import _native as N
+        self.wl, self.N = wl, N
+        sc = wl.sc
+        self.leaf = {k: sc[k].detach().clone().requires_grad_(True)
+                     for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        shapes = {k: tuple(v.shape) for k, v in self.leaf.items()}
+        shapes.update(means2D=(wl.P, 3), means2D_abs=(wl.P, 3))
+        self.arena = PL.GradArena(shapes, device=wl.device)
+        self.m2d = torch.zeros((wl.P, 3), device=wl.device, requires_grad=True)
+        self.m2a = torch.zeros((wl.P, 3), device=wl.device, requires_grad=True)
+        for k, v in self.leaf.items():
+            v.grad = self.arena.views[k]
+        self.m2d.grad = self.arena.views["means2D"]
+        self.m2a.grad = self.arena.views["means2D_abs"]
+        self.last_R = 0
+
+    def view_fwd_bwd(self, sc):
+        dpr, U = self.wl.dpr, self.wl.U
+        rs = U.make_settings(dpr, sc, render_geo=True)
+        am = sc["all_map"].detach().requires_grad_(True)
+        res = dpr.GaussianRasterizer(rs)(means3D=self.leaf["means3D"], means2D=self.m2d, means2D_abs=self.m2a,
+                                         opacities=self.leaf["opacities"], shs=self.leaf["shs"],
+                                         scales=self.leaf["scales"], rotations=self.leaf["rotations"], all_map=am)
+        cot = self.wl.cot
+        torch.autograd.backward([res[0], res[2], res[3], res[5]],
+                                [cot["color"], cot["normal"], cot["depth"], cot["warped"]])
+        return res[0]
+
+    def launches(self):
+        return int(self.N.lib.ibgs_launch_count())
+
+
+class RefRunner:
+    name = "reference"
+
+    def __init__(self, wl):
+        from ibgs_b200 import parallel as PL
+        from oracle import ref_ext
+        self.wl, self.ref = wl, ref_ext
+        ref_ext.load("dpr")
+        sc = wl.sc
+        shapes = {k: tuple(sc[k].shape) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        shapes.update(means2D=(wl.P, 3), means2D_abs=(wl.P, 3))
+        self.arena = PL.GradArena(shapes, device=wl.device)
+
+    def view_fwd_bwd(self, sc):
+        fw = self.ref.forward(sc, render_geo=True)
+        gr = self.ref.backward(sc, fw, self.wl.cot, render_geo=True)
+        self.arena.accumulate({"means3D": gr["means3D"], "shs": gr["sh"], "opacities": gr["opacities"],
+                               "scales": gr["scales"], "rotations": gr["rotations"], "means2D": gr["means2D"],
+                               "means2D_abs": gr["means2D_abs"]})
+        return fw["color"]
+
+    def launches(self):
+        return 0
+
+
+def run_steps(runner, wl, steps, world, e2e=False, stager=None):
+    """K steps; returns the last colour image's checksum tensor (device)."""
+    loss = None
+    for _ in range(steps):
+        runner.arena.zero_()
+        for vi, cam in enumerate(wl.views):
+            if e2e:
+                simg, sdep, cam_d = stager.fetch(vi)
+                cam2 = dict(cam)
+                cam2.update(cam_d)
+                sc = wl.scene_for(cam2, simg, sdep)
+            else:
+                sc = wl.scene_for(cam)
+            color = runner.view_fwd_bwd(sc)
+            if e2e:
+                stager.release(vi)
+        if world > 1:
+            runner.arena.all_reduce()
+        if e2e:
+            loss = float((color * wl.cot["color"]).sum().item())   # D2H read of the step's scalar result
+    return loss
+
+
+class HostStager:
+    """Pinned-host copies of every view's per-step inputs + double-buffered H2D prefetch on a copy stream."""
+
+    def __init__(self, wl):
+        self.wl = wl
+        dev = wl.device
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.host = []
+        for cam in wl.views:
+            h = dict(src_images=wl.sc["src_images"].cpu().pin_memory(),
+                     src_depths=wl.sc["src_rendered_depths"].cpu().pin_memory(),
+                     viewmatrix=cam["viewmatrix"].cpu().pin_memory(), projmatrix=cam["projmatrix"].cpu().pin_memory(),
+                     campos=cam["campos"].cpu().pin_memory(), ref_to_src_list=cam["ref_to_src_list"].cpu().pin_memory(),
+                     src_cam_pos=wl.sc["src_cam_pos"].cpu().pin_memory())
+            self.host.append(h)
+        self.nbuf = 2
+        self.dev = [{k: torch.empty_like(v, device=dev) for k, v in self.host[0].items()} for _ in range(self.nbuf)]
+        self.ready = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.free = [torch.cuda.Event() for _ in range(self.nbuf)]
+        self.bytes_per_view = sum(v.numel() * v.element_size() for v in self.host[0].values())
+        self.counter = 0
+        self.issued = -1
+        for e in self.free:
+            e.record(torch.cuda.current_stream(dev))
+
+    def _issue(self, n):
+        b = n % self.nbuf
+        vi = n % len(self.host)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.free[b])
+            for k, v in self.host[vi].items():
+                self.dev[b][k].copy_(v, non_blocking=True)
+            self.ready[b].record(self.copy_stream)
+        self.issued = n
+
+    def fetch(self, vi):
+        n = self.counter
+        if self.issued < n:
+            self._issue(n)
+        if self.issued < n + 1:
+            self._issue(n + 1)          # prefetch the next view while this one computes
+        b = n % self.nbuf
+        torch.cuda.current_stream(self.wl.device).wait_event(self.ready[b])
+        d = self.dev[b]
+        cam = {k: d[k] for k in ("viewmatrix", "projmatrix", "campos", "ref_to_src_list")}
+        return d["src_images"], d["src_depths"], cam
+
+    def release(self, vi):
+        b = self.counter % self.nbuf
+        self.free[b].record(torch.cuda.current_stream(self.wl.device))
+        self.counter += 1
+
+
+def timed(runner, wl, steps, warmup, world, e2e=False, stager=None):
+    dev = wl.device
+    run_steps(runner, wl, warmup, world, e2e, stager)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(runner, wl, steps, world, e2e, stager)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def cpu_baseline(args):
+    """Float64 CPU oracle (oracle/ibgs_oracle.c, OpenMP) on a bounded sample of the same workload."""
+    from ibgs_b200 import synthetic as S
+    from oracle import oracle as O
+    P0, W, H, _ = S.CONFIGS[args.config]
+    Ps = min(P0, 300_000)
+    sc = S.make_scene(args.config, P=Ps)
+    sc["src_rendered_depths"] = torch.full((4, 1, H, W), 4.0)
+    cot = S.cotangents(sc)
+    t = time.perf_counter()
+    fw = O.forward(sc)
+    O.backward(sc, fw, cot)
+    dt = time.perf_counter() - t
+    scale = P0 / Ps
+    return {"value": 1.0 / (dt * scale), "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"first-{Ps}-Gaussian subsample of the {P0}-Gaussian scene at {W}x{H}, 1 view fwd+bwd in "
+                      f"{dt:.2f}s, scaled x{scale:.0f} (linear in P); float64 C oracle with OpenMP"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and rank != 0:
+        return 0                                     # the reference is single-GPU; only rank 0 runs it
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": args.impl, "error": "no CUDA device: the rasterizer has no CPU path"}))
+        return 1
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    eff_world = 1 if args.impl == "reference" else world
+    if eff_world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from ibgs_b200 import synthetic as S
+    from ibgs_b200 import _native as N
+    wl = Workload(args, rank if eff_world > 1 else 0, eff_world, device, None)
+    kind = "reference"
+    if args.impl == "reference":
+        from oracle import ref_ext
+        if not ref_ext.available("dpr"):
+            cb = cpu_baseline(args)
+            line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "views/s", "n_gpus": args.gpus,
+                    "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+                    "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": args.config}, "cpu_baseline": cb,
+                    "e2e": {"value": cb["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+            return 0
+        runner = RefRunner(wl)
+    else:
+        runner = OursRunner(wl)
+        N.lib.ibgs_profile_enable(1)
+
+    V = args.views_per_step
+    # ---- device-resident arm ---------------------------------------------------------------------------
+    sampler, spath = start_clock_sampler(local_rank) if rank == 0 else (None, "")
+    N.lib.ibgs_profile_reset()
+    l0 = runner.launches()
+    ms = timed(runner, wl, args.steps, args.warmup, eff_world)
+    launches = (runner.launches() - l0) * args.steps // (args.steps + args.warmup) if args.impl == "b200" else None
+    stages = N.profile_read() if args.impl == "b200" else {}
+    clocks = stop_clock_sampler(sampler, spath) if rank == 0 else {}
+    views = eff_world * V * args.steps
+    value = views / (ms / 1000.0)
+
+    # ---- end-to-end arm (host buffers) -------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        N.lib.ibgs_profile_enable(0)
+        stager = HostStager(wl)
+        ms_e = timed(runner, wl, args.steps, args.warmup, eff_world, e2e=True, stager=stager)
+        e2e = {"value": views / (ms_e / 1000.0), "unit": "views/s",
+               "h2d_bytes_per_step": int(stager.bytes_per_view * V), "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e / args.steps}
+
+    if rank != 0:
+        if eff_world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- bookkeeping ---------------------------------------------------------------------------------------
+    wl.dpr.KEEP_STATE = True
+    with torch.no_grad():
+        sc0 = wl.scene_for(wl.views[0])
+        rs = wl.U.make_settings(wl.dpr, sc0, render_geo=True)
+        z = torch.zeros_like(sc0["means3D"])
+        wl.dpr.GaussianRasterizer(rs)(means3D=sc0["means3D"], means2D=z, means2D_abs=z, opacities=sc0["opacities"],
+                                      shs=sc0["shs"], scales=sc0["scales"], rotations=sc0["rotations"],
+                                      all_map=sc0["all_map"])
+    wl.dpr.KEEP_STATE = False
+    st = wl.dpr.LAST_STATE
+    R = int(st["num_rendered"])
+    dec = wl.U.decode_ours(st)
+    pairs = int(dec["n_contrib"].long().sum().item())          # upper bound on blended pairs (last contributor idx)
+    P_vis = int((dec["tiles_touched"] > 0).sum().item())
+    Npix = wl.W * wl.H
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    roofline = None
+    if args.impl == "b200" and stages.get("render_backward", (0, 0))[1] > 0:
+        bw_ms, bw_n = stages["render_backward"]
+        per_launch_ms = bw_ms / bw_n
+        # algorithmic bytes of the backward tile renderer: point list + one 64 B record
+        # read and one 64 B accumulator write per visible Gaussian + 212 B per pixel of cotangents / saved state
+        alg = 4 * R + 128 * P_vis + 212 * Npix
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("bytes_per_launch")
+        except Exception:
+            pass
+        ach = alg / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "render_backward_kernel<geo>", "achieved": ach, "peak": peak_gbs,
+                    "unit": "GB/s", "frac": ach / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
+                    "note": "the pair loop is issue/latency bound, not HBM bound (DESIGN.md): see pairs_per_s"}
+    bytes_view = 730 * wl.P + 28 * R + 460 * Npix              # SURVEY.md section 8d whole-view figure
+    ms_view = ms / (V * args.steps)
+    line = {
+        "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus if args.impl == "b200" else 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {wl.P} Gaussians, {wl.W}x{wl.H}, render_geo, 4 src views, sh_degree 2, "
+                               f"buffer_length 4", "views_per_step_per_gpu": V, "num_rendered_R": R,
+                   "visible_gaussians": P_vis, "sum_n_contrib": pairs,
+                   "l2": "per-view working set (192 MB records + 456 MB inputs + lists) exceeds the 126 MB L2; no flush",
+                   "parallelism": f"dp{eff_world} over views, replicated Gaussians, 1 all-reduce of "
+                                  f"{runner.arena.nbytes / 1e6:.0f} MB per step" if eff_world > 1 else "single GPU"},
+        "ms_per_view": ms_view,
+        "view_roofline": {"algorithmic_bytes_per_view": bytes_view, "achieved_GBps": bytes_view / (ms_view * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": bytes_view / (ms_view * 1e-3) / 1e9 / peak_gbs},
+        "pairs_per_s": pairs / (ms_view * 1e-3),
+        "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roofline,
+        "stages_ms_per_launch": {k: (v[0] / v[1] if v[1] else None) for k, v in stages.items()},
+    }
+    if args.impl == "reference":
+        line["impl"] = "reference"
+        line["gpu_launches"] = None
+        line["cpu_baseline"] = {"kind": kind, "cores": 0, "value": value, "unit": "views/s",
+                                "sample": "the reference has no CPU path: this arm is its unmodified CUDA extension "
+                                          "(oracle/_ref) on the same GPU, full workload"}
+    elif args.gpus == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line))
+    if eff_world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

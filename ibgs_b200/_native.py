@@ -64,7 +64,8 @@ class IbgsBackwardArgs(C.Structure):
 EXPORTS = [
     "ibgs_forward", "ibgs_backward", "ibgs_mark_visible", "ibgs_dist2_scratch_bytes", "ibgs_dist2",
     "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
-    "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached",
+    "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
+    "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages",
 ]
 
 
@@ -98,6 +99,14 @@ def _load():
     lib.ibgs_abi_version.restype = C.c_int
     lib.ibgs_launch_count.restype = C.c_int64
     lib.ibgs_release_cached.restype = None
+    lib.ibgs_profile_enable.restype = None
+    lib.ibgs_profile_enable.argtypes = [C.c_int]
+    lib.ibgs_profile_reset.restype = None
+    lib.ibgs_profile_read.restype = C.c_int
+    lib.ibgs_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.ibgs_profile_name.restype = C.c_char_p
+    lib.ibgs_profile_name.argtypes = [C.c_int]
+    lib.ibgs_profile_stages.restype = C.c_int
     return lib
 
 
@@ -112,6 +121,16 @@ def check(rc, what):
     if rc < 0:
         raise RuntimeError(f"{what} failed ({rc}): {last_error()}")
     return rc
+
+
+def profile_read():
+    """{stage name: (total ms, launches)} from the library's built-in event timer."""
+    out = {}
+    for i in range(lib.ibgs_profile_stages()):
+        ms, n = C.c_double(0), C.c_int64(0)
+        lib.ibgs_profile_read(i, C.byref(ms), C.byref(n))
+        out[lib.ibgs_profile_name(i).decode()] = (ms.value, n.value)
+    return out
 
 
 def state_layout(which, count, aux=0):

@@ -19,6 +19,68 @@ thread_local char g_err[1024] = "";
 int32_t* g_pinned_count = nullptr;  // pinned host word for the num_rendered read-back
 }  // namespace
 
+// ---- per-stage event timer -------------------------------------------------------------------------
+namespace {
+struct ProfPair { cudaEvent_t a, b; int id; };
+bool g_prof_on = false;
+std::vector<ProfPair> g_prof_pending;
+std::vector<ProfPair> g_prof_free;
+ProfPair g_prof_open[PROF_COUNT];
+bool g_prof_is_open[PROF_COUNT] = {false};
+double g_prof_ms[PROF_COUNT] = {0};
+long long g_prof_n[PROF_COUNT] = {0};
+const char* g_prof_names[PROF_COUNT] = {"preprocess", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
+                                        "texture_fill", "render_forward", "render_backward", "preprocess_backward"};
+void prof_drain() {
+  for (auto& p : g_prof_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      g_prof_ms[p.id] += ms;
+      g_prof_n[p.id] += 1;
+    }
+    g_prof_free.push_back(p);
+  }
+  g_prof_pending.clear();
+}
+}  // namespace
+
+void prof_begin(int id, cudaStream_t s) {
+  if (!g_prof_on) return;
+  ProfPair p;
+  if (!g_prof_free.empty()) {
+    p = g_prof_free.back();
+    g_prof_free.pop_back();
+  } else {
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+  }
+  p.id = id;
+  cudaEventRecord(p.a, s);
+  g_prof_open[id] = p;
+  g_prof_is_open[id] = true;
+}
+void prof_end(int id, cudaStream_t s) {
+  if (!g_prof_on || !g_prof_is_open[id]) return;
+  cudaEventRecord(g_prof_open[id].b, s);
+  g_prof_pending.push_back(g_prof_open[id]);
+  g_prof_is_open[id] = false;
+  if (g_prof_pending.size() > 4096) prof_drain();
+}
+extern "C" void ibgs_profile_enable(int on) { g_prof_on = on != 0; }
+extern "C" void ibgs_profile_reset(void) {
+  prof_drain();
+  for (int i = 0; i < PROF_COUNT; i++) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
+}
+extern "C" int ibgs_profile_read(int id, double* ms_total, int64_t* count) {
+  if (id < 0 || id >= PROF_COUNT) return IBGS_EINVAL;
+  prof_drain();
+  if (ms_total) *ms_total = g_prof_ms[id];
+  if (count) *count = g_prof_n[id];
+  return IBGS_OK;
+}
+extern "C" const char* ibgs_profile_name(int id) { return (id >= 0 && id < PROF_COUNT) ? g_prof_names[id] : ""; }
+extern "C" int ibgs_profile_stages(void) { return PROF_COUNT; }
+
 void ibgs_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -227,6 +289,7 @@ extern "C" int ibgs_backward(IbgsBackwardArgs* a, void* stream_v) {
   float4* arena = (float4*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, arena_bytes);
   if (!arena) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
   CUDA_TRY(cudaMemsetAsync(arena, 0, arena_bytes, s));
+  COUNT_LAUNCH();
 
   TexPair tex = {0, 0};
   if (v.render_geo) {

@@ -118,6 +118,7 @@ size_t scan_temp_bytes(size_t P) {
 }
 
 int run_scan(const GeomState& g, size_t P, void* temp, size_t temp_bytes, cudaStream_t s) {
+  ProfScope prof(PROF_SCAN, s);
   CUDA_TRY(cub::DeviceScan::InclusiveSum(temp, temp_bytes, g.tiles_touched, g.point_offsets, (int)P, s));
   g_launch_count += 2;
   return IBGS_OK;
@@ -148,20 +149,27 @@ int run_binning(const IbgsForwardArgs& a, const GeomState& g, const ImageState& 
     ibgs_set_error("scratch too small: %zu < %zu", scratch_bytes, need);
     return IBGS_EINVAL;
   }
-  duplicate_with_keys_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, g.rec, g.depths, g.point_offsets,
-                                                               sc.keys_unsorted, sc.vals_unsorted, a.radii,
-                                                               grid);
-  KERNEL_CHECK(debug, s);
+  {
+    ProfScope prof(PROF_DUPLICATE, s);
+    duplicate_with_keys_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, g.rec, g.depths, g.point_offsets,
+                                                                 sc.keys_unsorted, sc.vals_unsorted, a.radii,
+                                                                 grid);
+    KERNEL_CHECK(debug, s);
+  }
   if (R > 0) {
+    ProfScope prof(PROF_SORT, s);
     CUDA_TRY(cub::DeviceRadixSort::SortPairs(sc.sort_temp, sc.sort_temp_bytes, sc.keys_unsorted,
                                              sc.keys_sorted, sc.vals_unsorted, b.point_list, (int)R, 0,
                                              end_bit, s));
     g_launch_count += (end_bit + 7) / 8 + 1;
   }
-  CUDA_TRY(cudaMemsetAsync(im.ranges, 0, (size_t)grid.x * grid.y * sizeof(uint2), s));
-  if (R > 0) {
-    identify_tile_ranges_kernel<<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, sc.keys_sorted, im.ranges);
-    KERNEL_CHECK(debug, s);
+  {
+    ProfScope prof(PROF_RANGES, s);
+    CUDA_TRY(cudaMemsetAsync(im.ranges, 0, (size_t)grid.x * grid.y * sizeof(uint2), s));
+    if (R > 0) {
+      identify_tile_ranges_kernel<<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, sc.keys_sorted, im.ranges);
+      KERNEL_CHECK(debug, s);
+    }
   }
   return IBGS_OK;
 }

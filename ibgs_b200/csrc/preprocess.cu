@@ -278,6 +278,7 @@ int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, float focal_
   a.grid = grid;
   a.prefiltered = f.view.prefiltered;
   a.render_depth_only = f.view.render_depth_only;
+  ProfScope prof(PROF_PREPROCESS, s);
   preprocess_kernel<<<(f.P + 255) / 256, 256, 0, s>>>(a);
   KERNEL_CHECK(f.view.debug, s);
   return IBGS_OK;

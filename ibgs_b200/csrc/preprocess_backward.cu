@@ -390,6 +390,7 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.dL_dscales = f.dL_dscales;
   a.dL_drotations = f.dL_drotations;
   a.dL_dall_map = f.dL_dall_map;
+  ProfScope prof(PROF_PREPROCESS_BWD, s);
   preprocess_backward_kernel<<<(f.P + 255) / 256, 256, 0, s>>>(a);
   KERNEL_CHECK(f.view.debug, s);
   return IBGS_OK;

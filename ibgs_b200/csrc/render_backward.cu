@@ -413,6 +413,7 @@ int launch_render_backward(const IbgsBackwardArgs& f, const GeomState& g, const 
   a.dL_ddepths = f.dL_dout_median_intersected_depth;
   a.dL_dwarped = f.dL_dout_warped_image;
   a.arena = arena;
+  ProfScope prof(PROF_RENDER_BWD, s);
   if (f.view.render_geo)
     render_backward_kernel<true><<<grid, 256, 0, s>>>(a);
   else

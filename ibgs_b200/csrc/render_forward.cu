@@ -409,6 +409,7 @@ int launch_render_forward(const IbgsForwardArgs& f, const GeomState& g, const Im
   fa.out_mask = f.out_use_first_src_frame;
 
   int rc;
+  ProfScope prof(PROF_RENDER_FWD, s);
   // the reference evaluates render_geo before render_depth_only inside one kernel; with both set it
   // does both (forward.cu:445,466).  That combination is never produced by the callers
   // (gaussian_renderer/__init__.py:94-116,277-299); render_geo wins here.

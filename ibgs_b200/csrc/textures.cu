@@ -122,6 +122,7 @@ int textures_acquire(int W, int H, int layers, const float* src_images, const fl
   if (!reuse) {
     dim3 block(128, 1, 1);
     dim3 grid((W + 127) / 128, H, layers);
+    ProfScope prof(PROF_TEXFILL, s);
     fill_layers_kernel<<<grid, block, 0, s>>>(src_images, src_depths, W, H, layers, e->color_surf,
                                               e->depth_surf);
     KERNEL_CHECK(0, s);

@@ -177,6 +177,15 @@ const char* ibgs_last_error(void);
 int ibgs_abi_version(void);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches counter). */
 int64_t ibgs_launch_count(void);
+/* Built-in per-stage timer.  When enabled, every stage launched by ibgs_forward / ibgs_backward is
+ * bracketed by CUDA events on the launching stream; ibgs_profile_read(stage, &ms, &n) returns the summed
+ * device time and the number of timed launches (it waits for pending events).  Stage ids are
+ * 0..ibgs_profile_stages()-1, named by ibgs_profile_name. */
+void ibgs_profile_enable(int on);
+void ibgs_profile_reset(void);
+int ibgs_profile_read(int stage, double* ms_total, int64_t* count);
+const char* ibgs_profile_name(int stage);
+int ibgs_profile_stages(void);
 /* Releases cached textures / arenas. */
 void ibgs_release_cached(void);
 

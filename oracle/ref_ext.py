@@ -41,9 +41,13 @@ def _e(device):
 
 
 def forward(sc, render_geo=True, render_depth_only=False, buffer_length=4, depth_error_threshold=0.01,
-            colors_precomp=None, cov3D_precomp=None, debug=False):
-    """sc: dict of CUDA tensors (see tests/util.scene_to_device).  Returns dict(outputs..., state...)."""
+            colors_precomp=None, cov3D_precomp=None, debug=False, cam=None):
+    """sc: dict of CUDA tensors (see tests/ibgs_testutil.scene_to_device).  `cam` optionally overrides the
+    camera tensors + all_map (source-view depth renders).  Returns dict(outputs..., state...)."""
     C = load("dpr")
+    if cam is not None:
+        sc = dict(sc)
+        sc.update({k: cam[k] for k in ("viewmatrix", "projmatrix", "campos", "tanfovx", "tanfovy", "all_map")})
     dev = sc["means3D"].device
     sh = sc["shs"] if colors_precomp is None else _e(dev)
     colors = colors_precomp if colors_precomp is not None else _e(dev)

@@ -1,0 +1,167 @@
+"""GPU: the CUDA path (through the public API -> C ABI) against (a) the CPU oracle on the same seeded inputs,
+(b) the committed reference golden fixtures, and (c) size-independent properties at the full benchmark size."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from ibgs_b200 import synthetic as S
+import ibgs_testutil as U
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def dpr():
+    import ibgs_b200.diff_plane_rasterization as d
+    return d
+
+
+def test_cuda_matches_reference_golden_fixture(dpr):
+    """tests/golden/ref_tiny.npz was produced by the reference extension: integers exact, floats <= 1e-4."""
+    g = np.load(os.path.join(GOLD, "ref_tiny.npz"))
+    sc = U.scene_to_device(S.make_scene("tiny"))
+    sc["src_rendered_depths"] = torch.from_numpy(g["src_rendered_depths"]).cuda()
+    ours_src = U.render_src_depths(dpr, sc)
+    assert (ours_src.cpu().numpy() - g["src_rendered_depths"]).__abs__().max() <= 1e-4
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    outs, grads, state = U.ours_forward_backward(dpr, sc, cot, depth_error_threshold=float(g["thr"]))
+    assert state["num_rendered"] == int(g["num_rendered"])
+    assert np.array_equal(outs["radii"].cpu().numpy(), g["radii"])
+    st = U.decode_ours(state)
+    assert np.array_equal(st["n_contrib"].cpu().numpy(), g["n_contrib"])
+    assert np.array_equal(st["final_T"].cpu().numpy().view(np.int32), g["final_T"].view(np.int32))
+    assert np.array_equal(outs["mask"].cpu().numpy().astype(np.uint8), g["mask"])
+    for k in ("color", "normal", "depth", "cam_feat", "warped", "min_depth_diff", "camera_ray"):
+        assert np.abs(outs[k].cpu().numpy() - g["out_" + k]).max() <= 1e-4, k
+    for k in U.GRAD_NAMES:
+        a = grads[k].cpu().numpy().astype(np.float64)
+        b = g["grad_" + k].astype(np.float64).reshape(a.shape)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) <= 1e-3, k
+    for bl in (1, 3, 4):
+        o, _, _ = U.ours_forward_backward(dpr, sc, None, render_geo=False, render_depth_only=True, buffer_length=bl)
+        assert np.abs(o["depth"].cpu().numpy() - g[f"depth_only_bl{bl}"]).max() <= 1e-4
+
+
+def test_cuda_matches_cpu_oracle(dpr):
+    from oracle import oracle as O
+    sc_cpu = S.make_scene("cfg1")
+    sc = U.scene_to_device(sc_cpu)
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    sc_cpu["src_rendered_depths"] = sc["src_rendered_depths"].cpu()
+    cot_cpu = S.cotangents(sc_cpu)
+    cot = {k: v.cuda() for k, v in cot_cpu.items()}
+    outs, grads, state = U.ours_forward_backward(dpr, sc, cot)
+    fw = O.forward(sc_cpu)
+    gr = O.backward(sc_cpu, fw, cot_cpu)
+    assert state["num_rendered"] == fw.num_rendered
+    assert np.array_equal(outs["radii"].cpu().numpy(), fw.radii)
+    st = U.decode_ours(state)
+    assert np.array_equal(st["point_list"].cpu().numpy().astype(np.uint32), fw.point_list)
+    assert np.array_equal(st["ranges"].cpu().numpy().astype(np.uint32), fw.ranges)
+    assert (st["n_contrib"].cpu().numpy().astype(np.uint32) != fw.img["n_contrib"]).mean() < 5e-3
+    for k in ("color", "normal"):
+        d = np.abs(outs[k].cpu().numpy() - fw[k])
+        assert (d > 1e-4).mean() < 1e-3 and d.max() < 5e-3, k
+    for k, frac in (("camera_ray", 5e-3), ("depth", 5e-3), ("cam_feat", 5e-3), ("warped", 5e-3), ("min_depth_diff", 2e-2)):
+        d = np.abs(outs[k].cpu().numpy() - fw[k])
+        assert (d > 1e-3).mean() < frac, f"{k}: {(d > 1e-3).mean()}"
+    for k in U.GRAD_NAMES:
+        a = grads[k].cpu().numpy().astype(np.float64)
+        b = gr[k].reshape(a.shape)
+        a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+        err = np.abs(a2 - b2).sum(1)
+        keep = np.argsort(err)[: len(err) - max(1, len(err) // 100)]
+        rel = np.linalg.norm(a2[keep] - b2[keep]) / max(np.linalg.norm(b2[keep]), 1e-30)
+        assert rel < 5e-3, f"{k}: {rel}"
+
+
+def test_edge_cases(dpr):
+    sc = U.scene_to_device(S.make_scene("tiny"))
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    # P == 0: zero outputs, zero-sized grads, no crash (rasterize_points.cu:101-102)
+    sc0 = dict(sc)
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "all_map"):
+        sc0[k] = sc[k][:0].contiguous()
+    sc0["P"] = 0
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    outs, grads, state = U.ours_forward_backward(dpr, sc0, cot, keep_state=False)
+    assert outs["color"].abs().max().item() == 0 and outs["radii"].numel() == 0
+    assert grads["means3D"].shape == (0, 3)
+    # everything culled (behind the camera): R == 0, background only
+    sc1 = dict(sc)
+    sc1["means3D"] = (sc["means3D"] - 1000.0 * sc["w2c"][2, :3].cuda()).contiguous()
+    sc1["bg"] = torch.tensor([0.25, 0.5, 0.75], device="cuda")
+    outs, grads, state = U.ours_forward_backward(dpr, sc1, cot)
+    assert state["num_rendered"] == 0 and (outs["radii"] == 0).all()
+    assert torch.allclose(outs["color"][:, 3, 5], sc1["bg"])
+    assert grads["means3D"].abs().max().item() == 0
+    # ragged image size (not a multiple of the 16-pixel tile) and a single Gaussian
+    sc2 = U.scene_to_device(S.make_scene("tiny", W=37, H=23, P=1))
+    sc2["src_rendered_depths"] = U.render_src_depths(dpr, sc2)
+    outs, _, _ = U.ours_forward_backward(dpr, sc2, None)
+    assert outs["color"].shape == (3, 23, 37) and torch.isfinite(outs["color"]).all()
+    # precomputed colours / covariance path
+    from oracle import oracle as O
+    sc_cpu = S.make_scene("tiny")
+    fw = O.forward(dict(sc_cpu, src_rendered_depths=sc["src_rendered_depths"].cpu()))
+    rs = U.make_settings(dpr, sc, render_geo=False)
+    cov = torch.from_numpy(fw.geom["cov3D"]).float().cuda()
+    col = torch.rand((sc["P"], 3), device="cuda")
+    z = torch.zeros_like(sc["means3D"])
+    r1 = dpr.GaussianRasterizer(rs)(means3D=sc["means3D"], means2D=z, means2D_abs=z, opacities=sc["opacities"],
+                                    colors_precomp=col, cov3D_precomp=cov)
+    r2 = dpr.GaussianRasterizer(rs)(means3D=sc["means3D"], means2D=z, means2D_abs=z, opacities=sc["opacities"],
+                                    colors_precomp=col, scales=sc["scales"], rotations=sc["rotations"])
+    assert (r1[1] != r2[1]).float().mean().item() < 0.01          # radii (cov3D went through float64 -> float32)
+    assert (r1[0] - r2[0]).abs().mean().item() < 1e-3
+    # invalid buffer length is rejected by the C ABI
+    rs_bad = U.make_settings(dpr, sc, buffer_length=9)
+    with pytest.raises(RuntimeError, match="buffer_length"):
+        dpr.GaussianRasterizer(rs_bad)(means3D=sc["means3D"], means2D=z, means2D_abs=z, opacities=sc["opacities"],
+                                       shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"], all_map=sc["all_map"])
+
+
+def test_full_size_properties(dpr):
+    """BASELINE config 2 size (500k Gaussians @1080p): properties that need no oracle."""
+    sc = U.scene_to_device(S.make_scene("cfg2"))
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    outs, grads, state = U.ours_forward_backward(dpr, sc, cot)
+    st = U.decode_ours(state)
+    R, W, H = state["num_rendered"], sc["W"], sc["H"]
+    gx = (W + 15) // 16
+    keys = st["keys"]
+    assert bool((keys[1:] >= keys[:-1]).all())                                   # sortedness
+    assert int(st["point_offsets"][-1].item()) == R                              # scan total
+    assert int(st["tiles_touched"].long().sum().item()) == R
+    assert bool(((outs["radii"] > 0) == (st["tiles_touched"] > 0)).all())
+    rng = st["ranges"].long()
+    assert int((rng[:, 1] - rng[:, 0]).sum().item()) == R                        # ranges partition the list
+    tiles = (keys >> 32).long()
+    t_idx = torch.randint(0, rng.shape[0], (64,), device="cuda")
+    for t in t_idx.tolist():
+        a, b = rng[t].tolist()
+        if b > a:
+            assert int(tiles[a].item()) == t and int(tiles[b - 1].item()) == t
+    # stable sort == sort by (key, emission order): values of equal keys stay in Gaussian order
+    same = keys[1:] == keys[:-1]
+    assert bool((st["point_list"][1:][same] > st["point_list"][:-1][same]).all())
+    # determinism of the forward
+    outs2, _, _ = U.ours_forward_backward(dpr, sc, None)
+    for k in ("color", "normal", "depth", "warped", "cam_feat"):
+        assert torch.equal(outs[k], outs2[k]), k
+    # transmittance / background identity: render(bg=1) - render(bg=0) == final_T on every channel
+    sc_w = dict(sc, bg=torch.ones(3, device="cuda"))
+    outs_w, _, _ = U.ours_forward_backward(dpr, sc_w, None, render_geo=False, keep_state=False)
+    outs_b, _, state_b = U.ours_forward_backward(dpr, sc, None, render_geo=False)
+    T = U.decode_ours(state_b)["final_T"].view(H, W)
+    assert (outs_w["color"] - outs_b["color"] - T.unsqueeze(0)).abs().max().item() < 1e-5
+    assert float(T.min()) >= 0 and float(T.max()) <= 1
+    # linearity of the backward in the cotangents
+    cot2 = {k: 2.0 * v for k, v in cot.items()}
+    _, grads2, _ = U.ours_forward_backward(dpr, sc, cot2, keep_state=False)
+    for k in U.GRAD_NAMES:
+        assert U.rel_l2(grads2[k], 2.0 * grads[k]) < 1e-4, k

@@ -1,0 +1,96 @@
+"""CPU: host-side mirror of the reference's Python API (names, field order, error behaviour)."""
+import pytest
+import torch
+
+import ibgs_b200
+import ibgs_b200.diff_plane_rasterization as dpr
+
+# reference: submodules/diff-plane-rasterization/diff_plane_rasterization/__init__.py:252-276
+REFERENCE_SETTINGS_FIELDS = (
+    "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+    "ref_to_src_list", "src_cam_pos", "src_images", "src_rendered_depths", "nb_src_images", "buffer_length",
+    "depth_error_threshold", "sh_degree", "campos", "prefiltered", "render_geo", "render_depth_only", "debug")
+
+
+def _settings(**kw):
+    d = dict(image_height=8, image_width=8, tanfovx=0.5, tanfovy=0.5, bg=torch.zeros(3), scale_modifier=1.0,
+             viewmatrix=torch.eye(4), projmatrix=torch.eye(4), ref_to_src_list=torch.zeros(1, 16),
+             src_cam_pos=torch.zeros(1, 3), src_images=torch.zeros(1, 3, 64), src_rendered_depths=torch.zeros(1, 1, 64),
+             nb_src_images=1, buffer_length=4, depth_error_threshold=0.01, sh_degree=2, campos=torch.zeros(3),
+             prefiltered=False, render_geo=False, render_depth_only=False, debug=False)
+    d.update(kw)
+    return dpr.GaussianRasterizationSettings(**d)
+
+
+def test_settings_fields_match_reference_order():
+    assert dpr.GaussianRasterizationSettings._fields == REFERENCE_SETTINGS_FIELDS
+    assert isinstance(dpr.GaussianRasterizer(_settings()), torch.nn.Module)
+
+
+def test_forward_argument_validation_messages_match_reference():
+    r = dpr.GaussianRasterizer(_settings())
+    z = torch.zeros(4, 3)
+    # reference __init__.py:298-302
+    with pytest.raises(Exception, match="Please provide excatly one of either SHs or precomputed colors!"):
+        r(z, z, z, torch.zeros(4, 1), scales=z, rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="Please provide excatly one of either SHs or precomputed colors!"):
+        r(z, z, z, torch.zeros(4, 1), shs=torch.zeros(4, 9, 3), colors_precomp=z, scales=z, rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(z, z, z, torch.zeros(4, 1), shs=torch.zeros(4, 9, 3))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair or precomputed 3D covariance"):
+        r(z, z, z, torch.zeros(4, 1), shs=torch.zeros(4, 9, 3), scales=z, rotations=torch.zeros(4, 4),
+          cov3D_precomp=torch.zeros(4, 6))
+
+
+def test_bad_shape_and_cpu_tensors_raise():
+    r = dpr.GaussianRasterizer(_settings())
+    with pytest.raises(RuntimeError, match=r"means3D must have dimensions \(num_points, 3\)"):   # rasterize_points.cu:69-71
+        r(torch.zeros(4, 2), torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 1), shs=torch.zeros(4, 9, 3),
+          scales=torch.zeros(4, 3), rotations=torch.zeros(4, 4))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        z = torch.zeros(4, 3)
+        r(z, z, z, torch.zeros(4, 1), shs=torch.zeros(4, 9, 3), scales=z, rotations=torch.zeros(4, 4))
+    from ibgs_b200.simple_knn._C import distCUDA2
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        distCUDA2(torch.zeros(10, 3))
+
+
+def test_install_dropin_registers_reference_module_names():
+    import sys
+    saved = {k: sys.modules.get(k) for k in ("diff_plane_rasterization", "simple_knn", "simple_knn._C")}
+    try:
+        ibgs_b200.install_dropin()
+        from diff_plane_rasterization import GaussianRasterizationSettings, GaussianRasterizer  # noqa: F401
+        from simple_knn._C import distCUDA2  # noqa: F401  (scene/gaussian_model.py:20)
+        assert GaussianRasterizer is dpr.GaussianRasterizer
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_synthetic_scene_is_deterministic_and_consistent():
+    from ibgs_b200 import synthetic as S
+    a, b = S.make_scene("tiny"), S.make_scene("tiny")
+    for k in ("means3D", "scales", "rotations", "opacities", "shs", "all_map", "src_images", "ref_to_src_list"):
+        assert torch.equal(a[k], b[k]), k
+    # viewmatrix is the transpose of W2C; projecting a point in front of the camera lands inside NDC
+    w2c = a["w2c"]
+    assert torch.allclose(a["viewmatrix"], w2c.T)
+    p = torch.linalg.inv(w2c) @ torch.tensor([0.1, -0.2, 4.0, 1.0])
+    hom = p @ a["projmatrix"]
+    ndc = hom[:2] / hom[3]
+    assert ndc.abs().max() < 1.0
+    # all_map: unit normals facing the camera, positive distance column
+    am = a["all_map"]
+    assert torch.allclose(am[:, :3].norm(dim=1), torch.ones(am.shape[0]), atol=1e-5)
+    assert (am[:, 3] == 1).all() and (am[:, 4] >= 0).all()
+    # ref_to_src maps the reference camera centre to -R t of the relative pose: consistent with src_cam_pos
+    c_ref_world = torch.linalg.inv(w2c)[:3, 3]
+    for i in range(a["nb_src"]):
+        w2s = a["src_w2c"][i]
+        assert torch.allclose(a["ref_to_src_list"][i], w2s @ torch.linalg.inv(w2c), atol=1e-5)
+        assert torch.allclose(torch.linalg.inv(w2s)[:3, 3], a["src_cam_pos"][i], atol=1e-5)
+    assert c_ref_world.shape == (3,)

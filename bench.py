@@ -275,8 +275,16 @@ class HostStager:
         self.counter += 1
 
 
+PREWARM_STEPS = 6   # untimed set-up passes: let torch's caching allocator reach its steady state (the per-view
+                    # state buffers are tens of MB to GB; a cold cache means cudaMalloc + implicit syncs)
+
+
 def timed(runner, wl, steps, warmup, world, e2e=False, stager=None):
     dev = wl.device
+    run_steps(runner, wl, PREWARM_STEPS, world, e2e, stager)
+    torch.cuda.synchronize(dev)
+    import gc
+    gc.collect()
     run_steps(runner, wl, warmup, world, e2e, stager)
     if world > 1:
         dist.barrier()
@@ -347,15 +355,16 @@ def main():
         runner = RefRunner(wl)
     else:
         runner = OursRunner(wl)
-        N.lib.ibgs_profile_enable(1)
+        N.lib.ibgs_profile_enable(0 if os.environ.get("IBGS_BENCH_NOPROF") else 1)
 
     V = args.views_per_step
     # ---- device-resident arm ---------------------------------------------------------------------------
-    sampler, spath = start_clock_sampler(local_rank) if rank == 0 else (None, "")
+    sampler, spath = start_clock_sampler(local_rank) if (rank == 0 and not os.environ.get("IBGS_BENCH_NOCLOCK")) else (None, "")
     N.lib.ibgs_profile_reset()
     l0 = runner.launches()
     ms = timed(runner, wl, args.steps, args.warmup, eff_world)
-    launches = (runner.launches() - l0) * args.steps // (args.steps + args.warmup) if args.impl == "b200" else None
+    launches = ((runner.launches() - l0) * args.steps // (args.steps + args.warmup + PREWARM_STEPS)
+                if args.impl == "b200" else None)
     stages = N.profile_read() if args.impl == "b200" else {}
     clocks = stop_clock_sampler(sampler, spath) if rank == 0 else {}
     views = eff_world * V * args.steps

@@ -8,15 +8,21 @@
 // float atomicAdd per blended pair into per-Gaussian gradient arrays (:673,770,793-804).
 //
 // Kernel structure (this project's own):
-//   * one CTA per tile, warp = 8x4 pixel sub-tile, 64-byte records staged per batch as in the forward;
-//   * per warp, 32 Gaussians at a time are culled one-per-lane (alpha extent vs sub-tile, and
-//     contributor >= max n_contrib of the warp); only survivors are evaluated;
-//   * the 15 per-pair gradient terms are reduced across the 32 pixels of the warp with a
-//     value-splitting shuffle butterfly (16+8+4+2+1 = 31 shuffles for all 16 slots instead of 16x5),
-//     then 16 lanes add one slot each into a per-batch shared-memory accumulator (distinct banks);
-//   * after the batch each thread flushes ONE Gaussian's 64-byte accumulator with vector
-//     red.global.add.v4.f32 into a [P][16] arena -- at most 4 global atomics per (tile, Gaussian)
-//     instead of 16 per (pixel, Gaussian); untouched Gaussians are not flushed at all.
+//   * one CTA per tile, eight AUTONOMOUS warps (8x4 pixel sub-tile each) walking the tile list back to
+//     front, 32 instances per step, records fetched with cp.async into a per-warp double buffer -- no CTA
+//     barrier in the loop (see render_forward.cu); steps behind the warp's last contributor are skipped
+//     without being loaded;
+//   * each lane culls its own Gaussian (alpha extent vs sub-tile, contributor >= max n_contrib of the
+//     warp); only survivors are evaluated;
+//   * the 15 per-pair gradient terms are reduced across the 32 pixels of the warp with a value-splitting
+//     shuffle butterfly (16+8+4+2+1 = 31 shuffles for all 16 slots instead of 16x5) and 16 lanes then
+//     issue ONE red.global.add.f32 each into the Gaussian's 64-byte row of a [P][16] arena: one 64-byte
+//     reduction per (warp, surviving Gaussian) instead of 16 same-address atomics per (pixel, Gaussian);
+//   * the median-buffer terms (backward.cu:693-767: texture taps, per-view loops, per-pixel loads) touch
+//     at most buffer_length pairs per pixel but sit in the middle of the reference's pair loop, where they
+//     diverge the warp.  Here the pair loop only RECORDS those pairs (Gaussian id, T, colour/normal part of
+//     dL/dalpha); their whole gradient is evaluated afterwards in a dense per-pixel phase (every lane busy
+//     with its own entries) and added with vector reductions.
 // Summation order differs from the reference (which is itself run-to-run nondeterministic); the
 // parity gate for gradients is relative L2 <= 1e-3.
 #include "common.cuh"
@@ -121,18 +127,24 @@ __forceinline__ __device__ int slot_of_lane(int lane) {
   return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 // arena slots: 0,1 dmean2D.xy | 2,3 |dmean2D|.xy | 4,5,6 dconic x,y,w | 7 dopacity |
 //              8,9,10 dcolor | 11 dall_map[4] | 12,13,14 dall_map[0..2] | 15 unused
-template <bool GEO>
+// MAXE = number of median-buffer pairs a pixel can record (buffer_length + 1 spare for a pair that sits
+// exactly on the alpha threshold and is accepted by expf here but was rejected by __expf in the forward)
+template <bool GEO, int MAXE>
 __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ float4 s_q0[TILE_PIX];
-  __shared__ float4 s_q1[TILE_PIX];
-  __shared__ float4 s_q2[TILE_PIX];
-  __shared__ float4 s_q3[TILE_PIX];
-  __shared__ uint32_t s_id[TILE_PIX];
-  __shared__ int s_touched[TILE_PIX];
-  __shared__ __align__(16) float s_acc[TILE_PIX * 16];
+  __shared__ float4 s_rec[8][2][4][32];
   __shared__ float s_ref_to_src[MAX_SRC * 16];
 
   const int tid = threadIdx.x;
@@ -158,10 +170,10 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
   const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
   const int total = (int)(range.y - range.x);
 
-  if (GEO && tid < a.nb_src * 16) s_ref_to_src[tid] = a.ref_to_src_list[tid];
-#pragma unroll
-  for (int k = 0; k < 16; k++) s_acc[k * TILE_PIX + tid] = 0.0f;
-  s_touched[tid] = 0;
+  if (GEO) {
+    if (tid < a.nb_src * 16) s_ref_to_src[tid] = a.ref_to_src_list[tid];
+    __syncthreads();
+  }
 
   const float T_final = inside ? a.final_T[pix_id] : 0;
   float T = T_final;
@@ -194,28 +206,65 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
   const float ddelx_dx = 0.5 * W;  // backward.cu:606-607
   const float ddely_dy = 0.5 * H;
 
-  for (int base = 0; base < total; base += TILE_PIX) {
-    __syncthreads();  // accumulators zeroed / previous flush finished
-    const int cnt = min(TILE_PIX, total - base);
-    if (tid < cnt) {
-      // back to front: backward.cu:618
-      const uint32_t id = a.point_list[range.y - 1 - base - tid];
-      const float4* r = a.rec + 4 * (size_t)id;
-      s_id[tid] = id;
-      s_q0[tid] = __ldg(r + 0);
-      s_q1[tid] = __ldg(r + 1);
-      s_q2[tid] = __ldg(r + 2);
-      if (GEO) s_q3[tid] = __ldg(r + 3);
-    }
-    __syncthreads();
+  // recorded median-buffer pairs of this pixel
+  uint32_t ent_id[MAXE];
+  float ent_T[MAXE], ent_base[MAXE];
+  int ent_n = 0;
 
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
+  float* arena_f = reinterpret_cast<float*>(a.arena);
+  float4(*wrec)[4][32] = s_rec[warp];
+
+  // list position p (0 = back of the list) holds contributor index total-1-p; positions with
+  // contributor >= warp_max_contrib cannot contribute to any pixel of this warp: start after them
+  const int first_pos = total - (int)min((uint32_t)total, warp_max_contrib);
+  const int c_begin = first_pos >> 5;
+  const int nchunks = (total + 31) >> 5;
+  const uint32_t* plist_back = a.point_list + range.y - 1;  // plist_back[-p]
+
+  if (c_begin < nchunks) {
+    uint32_t id_next = 0u;  // id of this lane's Gaussian in the step being fetched
+    {
+      const int p = (c_begin << 5) + lane;
+      if (p < total) {
+        id_next = plist_back[-p];
+        const float4* r = a.rec + 4 * (size_t)id_next;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (k < 3 || GEO) cp_async16(&wrec[c_begin & 1][k][lane], r + k);
+      }
+      cp_async_commit();
+    }
+    uint32_t id_issue = 0u;
+    {
+      const int p = ((c_begin + 1) << 5) + lane;
+      if (p < total) id_issue = plist_back[-p];
+    }
+
+    for (int c = c_begin; c < nchunks; c++) {
+      const int buf = c & 1;
+      const int c0 = c << 5;
+      const uint32_t id_cur = id_next;
+      if (c + 1 < nchunks) {
+        id_next = id_issue;
+        if (c0 + 32 + lane < total) {
+          const float4* r = a.rec + 4 * (size_t)id_issue;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (k < 3 || GEO) cp_async16(&wrec[buf ^ 1][k][lane], r + k);
+        }
+        const int p2 = c0 + 64 + lane;
+        id_issue = (p2 < total) ? plist_back[-p2] : 0u;
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+
       const int j = c0 + lane;
       bool keep = false;
-      if (j < cnt) {
-        const uint32_t contributor_j = (uint32_t)(total - 1 - base - j);
-        const float4 q0 = s_q0[j];
-        const float4 q1 = s_q1[j];
+      if (j < total) {
+        const uint32_t contributor_j = (uint32_t)(total - 1 - j);
+        const float4 q0 = wrec[buf][0][lane];
+        const float4 q1 = wrec[buf][1][lane];
         const float ddx = fmaxf(fmaxf(wx0 - q0.x, q0.x - wx1), 0.0f);
         const float ddy = fmaxf(fmaxf(wy0 - q0.y, q0.y - wy1), 0.0f);
         keep = !(ddx > q1.z || ddy > q1.w) && (contributor_j < warp_max_contrib);
@@ -224,10 +273,9 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        const int jj = c0 + b;
-        const uint32_t contributor = (uint32_t)(total - 1 - base - jj);  // backward.cu:636
-        const float4 g0 = s_q0[jj];
-        const float4 g1 = s_q1[jj];
+        const uint32_t contributor = (uint32_t)(total - 1 - c0 - b);  // backward.cu:636
+        const float4 g0 = wrec[buf][0][b];
+        const float4 g1 = wrec[buf][1][b];
         const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
         const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
         const float G = expf(power);  // precise exp here, __expf in the forward (backward.cu:648)
@@ -235,6 +283,7 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
         const bool active = inside && !(contributor >= last_contributor) && !(power > 0.0f) &&
                             !(alpha < 1.0f / 255.0f);
         if (!__any_sync(FULL, active)) continue;
+        const uint32_t gid = __shfl_sync(FULL, id_cur, b);
 
         float v[16];
 #pragma unroll
@@ -244,7 +293,7 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
           T = T / (1.f - alpha);
           const float dchannel_dcolor = alpha * T;
           float dL_dalpha = 0.0f;
-          const float4 g2 = s_q2[jj];
+          const float4 g2 = wrec[buf][2][b];
           const float col[3] = {g2.x, g2.y, g2.z};
 #pragma unroll
           for (int ch = 0; ch < 3; ch++) {
@@ -255,10 +304,10 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
             dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
             v[8 + ch] = dchannel_dcolor * dL_dchannel;
           }
+          bool deferred = false;
           if (GEO) {
-            const float4 g3 = s_q3[jj];
+            const float4 g3 = wrec[buf][3][b];
             const float nrm[3] = {g3.x, g3.y, g3.z};
-            float dL_dall_map_temp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
               const float c = nrm[ch];
@@ -266,118 +315,146 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
               last_nrm[ch] = c;
               const float dL_dchannel = dL_dnormal[ch];
               dL_dalpha += (c - accum_nrm[ch]) * dL_dchannel;
-              dL_dall_map_temp[ch] += dchannel_dcolor * dL_dchannel;
+              v[12 + ch] = dchannel_dcolor * dL_dchannel;
             }
-            // median buffer, backward.cu:693-767 (unsigned comparison against int-1 as in the reference)
+            // median buffer, backward.cu:693-701 (unsigned comparison against int-1 as in the reference):
+            // a pair in range with a valid plane depth is only RECORDED here; see the dense phase below
             if ((contributor >= (uint32_t)(min_median_contributor - 1)) &&
                 (contributor <= (uint32_t)(max_median_contributor - 1))) {
-              const float3 normal_gauss = {g3.x, g3.y, g3.z};
-              const float distance_gauss = g2.w;
-              const float tmp_gauss =
-                  (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
-              const float tmp_gauss2 = distance_gauss / (tmp_gauss * tmp_gauss);
-              const float intersected_depth =
-                  -distance_gauss / (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
-              if (intersected_depth > 0.0f) {
-                const float3 ip = {(pixf.x - cx) * intersected_depth / fx,
-                                   (pixf.y - cy) * intersected_depth / fy, intersected_depth};
-                const float sumw = a.sum_w[pix_id];
-                float dL_dz = dL_ddepth * dchannel_dcolor / sumw;
-                dL_dalpha += dL_ddepth * (intersected_depth - a.depth_pixels[pix_id]) / sumw;
-                for (int mm = 0; mm < MAX_SRC; mm++) {
-                  const int src_idx = a.valid_idx[mm * HW + pix_id];
-                  if (src_idx == -1) break;
-                  const float* r2s = &s_ref_to_src[src_idx * 16];
-                  const float3 tp = {r2s[0] * ip.x + r2s[1] * ip.y + r2s[2] * ip.z + r2s[3],
-                                     r2s[4] * ip.x + r2s[5] * ip.y + r2s[6] * ip.z + r2s[7],
-                                     r2s[8] * ip.x + r2s[9] * ip.y + r2s[10] * ip.z + r2s[11]};
-                  const float2 pp = {(tp.x * fx / tp.z) + cx, (tp.y * fy / tp.z) + cy};
-                  if (pp.x >= 0 && pp.x <= W - 1 && pp.y >= 0 && pp.y <= H - 1) {
-                    const float4 texC = tex2DLayered<float4>(a.texColor, pp.x + 0.5f, pp.y + 0.5f, src_idx);
-                    const float wc[3] = {texC.x, texC.y, texC.z};
-                    const float vw = a.valid_w[mm * HW + pix_id];
-                    float dLc[3];
+              const float intersected_depth = -g2.w / (g3.x * ray.x + g3.y * ray.y + g3.z + 1.0e-8);
+              if (intersected_depth > 0.0f && ent_n < MAXE) {
 #pragma unroll
-                    for (int n_i = 0; n_i < 3; n_i++) {
-                      const float dLw = a.dL_dwarped[mm * 3 * HW + n_i * HW + pix_id];
-                      dLc[n_i] = dLw * dchannel_dcolor / vw;
-                      dL_dalpha += dLw * (wc[n_i] - a.warped_pixels[mm * 3 * HW + n_i * HW + pix_id]) / vw;
-                    }
-                    const float A_val = (pixf.x - cx) / fx;
-                    const float B_val = (pixf.y - cy) / fy;
-                    const float U = r2s[0] * A_val + r2s[1] * B_val + r2s[2];
-                    const float V = r2s[4] * A_val + r2s[5] * B_val + r2s[6];
-                    const float W_coeff = r2s[8] * A_val + r2s[9] * B_val + r2s[10];
-                    const float r0 = r2s[3], r1 = r2s[7], r2 = r2s[11];
-                    const float denom = (W_coeff * intersected_depth + r2);
-                    const float dp_x_dd = fx * (U * r2 - W_coeff * r0) / (denom * denom);
-                    const float dp_y_dd = fy * (V * r2 - W_coeff * r1) / (denom * denom);
-                    const float2 dpp = bilinearInterpolateBackward(src_idx, a.texColor, pp,
-                                                                   make_float3(dLc[0], dLc[1], dLc[2]));
-                    const float from_color = dpp.x * dp_x_dd + dpp.y * dp_y_dd;
-                    dL_dz += from_color;
-                    // accumulated inside the view loop, exactly like backward.cu:757-763
-                    dL_dall_map_temp[4] += (-dL_dz / tmp_gauss);
-                    dL_dall_map_temp[0] += dL_dz * tmp_gauss2 * ray.x;
-                    dL_dall_map_temp[1] += dL_dz * tmp_gauss2 * ray.y;
-                    dL_dall_map_temp[2] += dL_dz * tmp_gauss2;
-                  }
-                }
+                for (int k = 0; k < MAXE; k++)
+                  if (ent_n == k) { ent_id[k] = gid; ent_T[k] = T; ent_base[k] = dL_dalpha; }
+                ent_n++;
+                deferred = true;
               }
             }
-            v[12] = dL_dall_map_temp[0];
-            v[13] = dL_dall_map_temp[1];
-            v[14] = dL_dall_map_temp[2];
-            v[11] = dL_dall_map_temp[4];
           }
-
-          dL_dalpha *= T;
           last_alpha = alpha;
-          dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
-
-          const float dL_dG = g1.y * dL_dalpha;
-          const float gdx = G * d.x;
-          const float gdy = G * d.y;
-          const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-          const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-          v[0] = dL_dG * dG_ddelx * ddelx_dx;
-          v[1] = dL_dG * dG_ddely * ddely_dy;
-          v[2] = fabs(dL_dG * dG_ddelx * ddelx_dx);
-          v[3] = fabs(dL_dG * dG_ddely * ddely_dy);
-          v[4] = -0.5f * gdx * d.x * dL_dG;
-          v[5] = -0.5f * gdx * d.y * dL_dG;
-          v[6] = -0.5f * gdy * d.y * dL_dG;
-          v[7] = G * dL_dalpha;
+          if (!deferred) {
+            dL_dalpha *= T;
+            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+            const float dL_dG = g1.y * dL_dalpha;
+            const float gdx = G * d.x;
+            const float gdy = G * d.y;
+            const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+            const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+            v[0] = dL_dG * dG_ddelx * ddelx_dx;
+            v[1] = dL_dG * dG_ddely * ddely_dy;
+            v[2] = fabs(dL_dG * dG_ddelx * ddelx_dx);
+            v[3] = fabs(dL_dG * dG_ddely * ddely_dy);
+            v[4] = -0.5f * gdx * d.x * dL_dG;
+            v[5] = -0.5f * gdx * d.y * dL_dG;
+            v[6] = -0.5f * gdy * d.y * dL_dG;
+            v[7] = G * dL_dalpha;
+          }
         }
 
         warp_reduce16(v, lane);
         if ((lane & 1) == 0) {
           const int slot = slot_of_lane(lane);
-          // AoS accumulator, 16 floats per staged Gaussian; the float4 group index is XOR-swizzled by
-          // (jj>>1)&3 so the per-thread float4 flush below is bank-conflict free
-          if (GEO || slot < 12)
-            atomicAdd(&s_acc[jj * 16 + ((((slot >> 2) ^ (jj >> 1)) & 3) << 2) + (slot & 3)], v[0]);
+          if (GEO ? (slot != 11 && slot != 15) : (slot < 11)) atomicAdd(arena_f + 16 * (size_t)gid + slot, v[0]);
         }
-        if (lane == 0) s_touched[jj] = 1;
       }
+      __syncwarp();  // all lanes are done with buf before the step after next overwrites it
     }
+    cp_async_wait<0>();
+  }
 
-    __syncthreads();
-    // flush: one thread per staged Gaussian, vector reductions into the arena
-    if (tid < cnt && s_touched[tid]) {
-      float4* dst = a.arena + 4 * (size_t)s_id[tid];
-      float4* acc = reinterpret_cast<float4*>(s_acc) + tid * 4;
-      const int sw = (tid >> 1) & 3;
-      const float4 zero4 = {0.f, 0.f, 0.f, 0.f};
-      atomicAdd(dst + 0, acc[0 ^ sw]);
-      atomicAdd(dst + 1, acc[1 ^ sw]);
-      atomicAdd(dst + 2, acc[2 ^ sw]);
-      if (GEO) atomicAdd(dst + 3, acc[3 ^ sw]);
-      acc[0] = zero4;
-      acc[1] = zero4;
-      acc[2] = zero4;
-      acc[3] = zero4;
-      s_touched[tid] = 0;
+  // ---- dense per-pixel phase: the recorded median-buffer pairs (backward.cu:693-767, 773-804) ----
+  if (GEO && inside && ent_n > 0) {
+    const float sumw = a.sum_w[pix_id];
+    const float depth_pix = a.depth_pixels[pix_id];
+#pragma unroll 1
+    for (int e = 0; e < ent_n; e++) {
+      uint32_t gid = 0;
+      float Te = 0.f, base = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXE; k++)
+        if (e == k) { gid = ent_id[k]; Te = ent_T[k]; base = ent_base[k]; }
+      const float4* r = a.rec + 4 * (size_t)gid;
+      const float4 g0 = __ldg(r + 0), g1 = __ldg(r + 1), g2 = __ldg(r + 2), g3 = __ldg(r + 3);
+      const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
+      const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
+      const float G = expf(power);
+      const float alpha = min(0.99f, g1.y * G);
+      const float dchannel_dcolor = alpha * Te;
+      float dL_dalpha = base;
+      float dL_dall_map_temp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+
+      const float3 normal_gauss = {g3.x, g3.y, g3.z};
+      const float distance_gauss = g2.w;
+      const float tmp_gauss = (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
+      const float tmp_gauss2 = distance_gauss / (tmp_gauss * tmp_gauss);
+      const float intersected_depth =
+          -distance_gauss / (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
+      const float3 ip = {(pixf.x - cx) * intersected_depth / fx, (pixf.y - cy) * intersected_depth / fy,
+                         intersected_depth};
+      float dL_dz = dL_ddepth * dchannel_dcolor / sumw;
+      dL_dalpha += dL_ddepth * (intersected_depth - depth_pix) / sumw;
+      for (int mm = 0; mm < MAX_SRC; mm++) {
+        const int src_idx = a.valid_idx[mm * HW + pix_id];
+        if (src_idx == -1) break;
+        const float* r2s = &s_ref_to_src[src_idx * 16];
+        const float3 tp = {r2s[0] * ip.x + r2s[1] * ip.y + r2s[2] * ip.z + r2s[3],
+                           r2s[4] * ip.x + r2s[5] * ip.y + r2s[6] * ip.z + r2s[7],
+                           r2s[8] * ip.x + r2s[9] * ip.y + r2s[10] * ip.z + r2s[11]};
+        const float2 pp = {(tp.x * fx / tp.z) + cx, (tp.y * fy / tp.z) + cy};
+        if (pp.x >= 0 && pp.x <= W - 1 && pp.y >= 0 && pp.y <= H - 1) {
+          const float4 texC = tex2DLayered<float4>(a.texColor, pp.x + 0.5f, pp.y + 0.5f, src_idx);
+          const float wc[3] = {texC.x, texC.y, texC.z};
+          const float vw = a.valid_w[mm * HW + pix_id];
+          float dLc[3];
+#pragma unroll
+          for (int n_i = 0; n_i < 3; n_i++) {
+            const float dLw = a.dL_dwarped[mm * 3 * HW + n_i * HW + pix_id];
+            dLc[n_i] = dLw * dchannel_dcolor / vw;
+            dL_dalpha += dLw * (wc[n_i] - a.warped_pixels[mm * 3 * HW + n_i * HW + pix_id]) / vw;
+          }
+          const float A_val = (pixf.x - cx) / fx;
+          const float B_val = (pixf.y - cy) / fy;
+          const float U = r2s[0] * A_val + r2s[1] * B_val + r2s[2];
+          const float V = r2s[4] * A_val + r2s[5] * B_val + r2s[6];
+          const float W_coeff = r2s[8] * A_val + r2s[9] * B_val + r2s[10];
+          const float r0 = r2s[3], r1 = r2s[7], r2 = r2s[11];
+          const float denom = (W_coeff * intersected_depth + r2);
+          const float dp_x_dd = fx * (U * r2 - W_coeff * r0) / (denom * denom);
+          const float dp_y_dd = fy * (V * r2 - W_coeff * r1) / (denom * denom);
+          const float2 dpp = bilinearInterpolateBackward(src_idx, a.texColor, pp, make_float3(dLc[0], dLc[1], dLc[2]));
+          const float from_color = dpp.x * dp_x_dd + dpp.y * dp_y_dd;
+          dL_dz += from_color;
+          // accumulated inside the view loop, exactly like backward.cu:757-763
+          dL_dall_map_temp[4] += (-dL_dz / tmp_gauss);
+          dL_dall_map_temp[0] += dL_dz * tmp_gauss2 * ray.x;
+          dL_dall_map_temp[1] += dL_dz * tmp_gauss2 * ray.y;
+          dL_dall_map_temp[2] += dL_dz * tmp_gauss2;
+        }
+      }
+      dL_dalpha *= Te;
+      dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+      const float dL_dG = g1.y * dL_dalpha;
+      const float gdx = G * d.x;
+      const float gdy = G * d.y;
+      const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+      const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+      float4 f0, f1;
+      f0.x = dL_dG * dG_ddelx * ddelx_dx;
+      f0.y = dL_dG * dG_ddely * ddely_dy;
+      f0.z = fabs(dL_dG * dG_ddelx * ddelx_dx);
+      f0.w = fabs(dL_dG * dG_ddely * ddely_dy);
+      f1.x = -0.5f * gdx * d.x * dL_dG;
+      f1.y = -0.5f * gdx * d.y * dL_dG;
+      f1.z = -0.5f * gdy * d.y * dL_dG;
+      f1.w = G * dL_dalpha;
+      float4* dst = a.arena + 4 * (size_t)gid;
+      atomicAdd(dst + 0, f0);
+      atomicAdd(dst + 1, f1);
+      if (dL_dall_map_temp[4] != 0.f || dL_dall_map_temp[0] != 0.f || dL_dall_map_temp[1] != 0.f ||
+          dL_dall_map_temp[2] != 0.f) {
+        atomicAdd(arena_f + 16 * (size_t)gid + 11, dL_dall_map_temp[4]);
+        atomicAdd(dst + 3, make_float4(dL_dall_map_temp[0], dL_dall_map_temp[1], dL_dall_map_temp[2], 0.f));
+      }
     }
   }
 }
@@ -414,10 +491,14 @@ int launch_render_backward(const IbgsBackwardArgs& f, const GeomState& g, const 
   a.dL_dwarped = f.dL_dout_warped_image;
   a.arena = arena;
   ProfScope prof(PROF_RENDER_BWD, s);
-  if (f.view.render_geo)
-    render_backward_kernel<true><<<grid, 256, 0, s>>>(a);
-  else
-    render_backward_kernel<false><<<grid, 256, 0, s>>>(a);
+  if (f.view.render_geo) {
+    if (f.view.buffer_length <= 4)
+      render_backward_kernel<true, 5><<<grid, 256, 0, s>>>(a);
+    else
+      render_backward_kernel<true, 9><<<grid, 256, 0, s>>>(a);
+  } else {
+    render_backward_kernel<false, 1><<<grid, 256, 0, s>>>(a);
+  }
   KERNEL_CHECK(f.view.debug, s);
   return IBGS_OK;
 }

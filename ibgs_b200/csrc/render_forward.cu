@@ -6,16 +6,20 @@
 // depth-only variant (:466-489) and the multi-view warp epilogue (:512-663).
 //
 // Kernel structure (this project's own):
-//   * one CTA (256 threads) per tile; warp w owns an 8x4 pixel sub-tile (compact footprint);
-//   * batches of 256 tile instances are gathered as ONE 64-byte record per Gaussian into shared
-//     memory (4 x LDG.128 per thread, then 4 x STS.128) -- colour and plane parameters ride along, so
-//     the pair loop never touches global memory (the reference re-reads features/all_map from global
-//     for every blended pair, forward.cu:433-448);
-//   * each warp then tests 32 Gaussians at a time, one per lane, against its sub-tile with the
-//     conservative alpha>=1/255 extent stored in the record, ballots, and only walks the survivors;
-//     rejected Gaussians are exactly ones the reference would skip at forward.cu:425 for all 32 pixels,
-//     so per-pixel results are unchanged;
-//   * warp-level early termination (all 32 pixels done) on top of the reference's CTA-level one;
+//   * one CTA (256 threads) per tile, but the eight warps are AUTONOMOUS: warp w owns an 8x4 pixel
+//     sub-tile and walks the tile's sorted list on its own, 32 instances per step, with no CTA barrier
+//     in the loop (the reference synchronises the whole CTA twice per 256 instances, forward.cu:405,414,
+//     so every warp waits for the slowest one);
+//   * per step each lane fetches ONE 64-byte per-Gaussian record with cp.async (LDGSTS, L1-allocating so
+//     the other seven warps of the tile hit L1) into a per-warp double buffer in shared memory -- the
+//     copy of step c+1 is in flight while step c is blended; colour and plane parameters ride in the
+//     record, so the pair loop never touches global memory (the reference re-reads features / all_map
+//     from global for every blended pair, forward.cu:433-448);
+//   * each lane tests its own Gaussian against the warp's sub-tile with the conservative alpha>=1/255
+//     extent stored in the record, the warp ballots, and only the survivors are walked; rejected
+//     Gaussians are exactly ones the reference would skip at forward.cu:425 for all 32 pixels, so
+//     per-pixel results are unchanged;
+//   * warp-level early termination: a warp leaves as soon as its 32 pixels are done;
 //   * the median ring lives in registers (compile-time BL), not in a dynamically indexed local array
 //     (the reference kernel carries a 192-byte local stack for it).
 #include "common.cuh"
@@ -55,16 +59,24 @@ struct FwdArgs {
 
 enum { MODE_COLOR = 0, MODE_GEO = 1, MODE_DEPTH = 2 };
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
 template <int MODE, int BL>
 __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
   constexpr int BEFORE = (BL + 1) / 2;  // forward.cu:384
   constexpr int BELOW = BL - BEFORE;    // forward.cu:385
   constexpr unsigned FULL = 0xffffffffu;
 
-  __shared__ float4 s_q0[TILE_PIX];
-  __shared__ float4 s_q1[TILE_PIX];
-  __shared__ float4 s_q2[TILE_PIX];
-  __shared__ float4 s_q3[TILE_PIX];
+  // per-warp double buffer: [warp][buf][quad][lane]
+  __shared__ float4 s_rec[8][2][4][32];
   __shared__ float s_ref_to_src[MAX_SRC * 16];
   __shared__ float s_src_cam_pos[MAX_SRC * 3];
 
@@ -92,6 +104,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
   if (MODE == MODE_GEO) {
     if (tid < a.nb_src * 16) s_ref_to_src[tid] = a.ref_to_src_list[tid];
     if (tid < a.nb_src * 3) s_src_cam_pos[tid] = a.src_cam_pos[tid];
+    __syncthreads();  // the only CTA barrier: epilogue constants
   }
 
   const float epsilon = 1.0e-8f;
@@ -107,32 +120,48 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
   int below_count = 0;
   float total_buffer_weight = 0.0f;
   float weighted_depth_sum = 0.0f;
-  bool warp_done = false;
+  // depth-only with BELOW==0 (BL==1): the reference `break`s out of the current 256-instance batch only
+  // (forward.cu:484-488) and resumes with the next one
+  bool brk = false;
 
-  for (int base = 0; base < total; base += TILE_PIX) {
-    // CTA-level early exit (forward.cu:405); the barrier also fences re-use of the staging buffers
-    if (__syncthreads_and(done)) break;
-    const int cnt = min(TILE_PIX, total - base);
-    if (tid < cnt) {
-      const uint32_t id = a.point_list[range.x + base + tid];
-      const float4* r = a.rec + 4 * (size_t)id;
-      s_q0[tid] = __ldg(r + 0);
-      s_q1[tid] = __ldg(r + 1);
-      s_q2[tid] = __ldg(r + 2);
-      if (MODE != MODE_COLOR) s_q3[tid] = __ldg(r + 3);
+  const uint32_t* plist = a.point_list + range.x;
+  const int nchunks = (total + 31) >> 5;
+  float4(*wrec)[4][32] = s_rec[warp];
+
+  // software pipeline: ids two steps ahead (register), records one step ahead (cp.async)
+  uint32_t id_issue = (lane < total) ? plist[lane] : 0u;
+  if (nchunks > 0 && !__all_sync(FULL, done)) {
+    if (lane < total) {
+      const float4* r = a.rec + 4 * (size_t)id_issue;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k < 3 || MODE != MODE_COLOR) cp_async16(&wrec[0][k][lane], r + k);
     }
-    __syncthreads();
-    if (warp_done) continue;
-    // depth-only with BELOW==0 (BL==1): the reference `break`s out of the current batch only
-    // (forward.cu:484-488) and resumes with the next one
-    bool brk = false;
+    cp_async_commit();
+    id_issue = (32 + lane < total) ? plist[32 + lane] : 0u;
 
-    for (int c0 = 0; c0 < cnt; c0 += 32) {
+    for (int c = 0; c < nchunks; c++) {
+      const int buf = c & 1;
+      const int c0 = c << 5;
+      if (c + 1 < nchunks) {
+        if (c0 + 32 + lane < total) {
+          const float4* r = a.rec + 4 * (size_t)id_issue;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (k < 3 || MODE != MODE_COLOR) cp_async16(&wrec[buf ^ 1][k][lane], r + k);
+        }
+        id_issue = (c0 + 64 + lane < total) ? plist[c0 + 64 + lane] : 0u;
+      }
+      cp_async_commit();
+      cp_async_wait<1>();   // everything but the newest group has landed -> step c is in shared memory
+      __syncwarp();
+      if ((c0 & (TILE_PIX - 1)) == 0) brk = false;  // new 256-instance batch of the reference
+
       const int j = c0 + lane;
       bool keep = false;
-      if (j < cnt) {
-        const float4 q0 = s_q0[j];
-        const float4 q1 = s_q1[j];
+      if (j < total) {
+        const float4 q0 = wrec[buf][0][lane];
+        const float4 q1 = wrec[buf][1][lane];
         const float ddx = fmaxf(fmaxf(wx0 - q0.x, q0.x - wx1), 0.0f);
         const float ddy = fmaxf(fmaxf(wy0 - q0.y, q0.y - wy1), 0.0f);
         keep = !(ddx > q1.z || ddy > q1.w);
@@ -141,11 +170,10 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        const int jj = c0 + b;
         if (done || brk) continue;
-        const uint32_t contributor = (uint32_t)(base + jj + 1);  // forward.cu:417
-        const float4 g0 = s_q0[jj];
-        const float4 g1 = s_q1[jj];
+        const uint32_t contributor = (uint32_t)(c0 + b + 1);  // forward.cu:417
+        const float4 g0 = wrec[buf][0][b];
+        const float4 g1 = wrec[buf][1][b];
         const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
         // con_o = (g0.z, g0.w, g1.x, g1.y); forward.cu:421-427
         const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
@@ -156,14 +184,14 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
         if (test_T < 0.0001f) { done = true; continue; }
         const float aT = alpha * T;
 
-        const float4 g2 = s_q2[jj];
+        const float4 g2 = wrec[buf][2][b];
         if (MODE != MODE_DEPTH) {
           C[0] += g2.x * aT;
           C[1] += g2.y * aT;
           C[2] += g2.z * aT;
         }
         if (MODE != MODE_COLOR) {
-          const float4 g3 = s_q3[jj];
+          const float4 g3 = wrec[buf][3][b];
           // forward.cu:439-442
           const float intersected_depth = -g2.w / (g3.x * ray.x + g3.y * ray.y + g3.z + epsilon);
           if (MODE == MODE_GEO) {
@@ -216,8 +244,9 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
         T = test_T;
         last_contributor = contributor;
       }
-      if (__all_sync(FULL, done)) { warp_done = true; break; }
+      if (__all_sync(FULL, done)) break;   // warp-level early termination (also orders the buffer re-use)
     }
+    cp_async_wait<0>();
   }
 
   if (!inside) return;

@@ -79,6 +79,13 @@ class _Allocator:
             self.error = ex
             return None
 
+    def release(self):
+        """Break the allocator <-> ctypes-callback reference cycle so the scratch tensors return to torch's
+        caching allocator immediately (not at the next cyclic GC pass)."""
+        self.fn = None
+        self.scratch = []
+        self.bufs = {}
+
 
 def _fill_view(view, rs, device, sh_coeffs, keep):
     H, W = int(rs.image_height), int(rs.image_width)
@@ -201,6 +208,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             LAST_STATE.update(geom=geomBuffer, binning=binningBuffer, image=imgBuffer,
                               scratch=alloc.scratch[-1] if alloc.scratch else empty,
                               num_rendered=num_rendered, P=P, H=H, W=W)
+        a.alloc = N.ALLOC_FN()
+        alloc.release()
 
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
@@ -321,6 +330,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                     raise ex
             else:
                 run()
+            a.alloc = N.ALLOC_FN()
+            alloc.release()
 
         need = ctx.needs_input_grad
         grads = (

@@ -290,7 +290,10 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
         for (int k = 0; k < 16; k++) v[k] = 0.0f;
 
         if (active) {
-          T = T / (1.f - alpha);
+          // 1/(1-alpha) once, approximate reciprocal (2 ulp): gradients are compared at 1e-3 relative L2 and
+          // summed in a different order than the reference anyway
+          const float rinv = __fdividef(1.f, 1.f - alpha);
+          T = T * rinv;
           const float dchannel_dcolor = alpha * T;
           float dL_dalpha = 0.0f;
           const float4 g2 = wrec[buf][2][b];
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
           last_alpha = alpha;
           if (!deferred) {
             dL_dalpha *= T;
-            dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+            dL_dalpha += (-T_final * rinv) * bg_dot_dpixel;
             const float dL_dG = g1.y * dL_dalpha;
             const float gdx = G * d.x;
             const float gdy = G * d.y;
@@ -364,8 +367,30 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
 
   // ---- dense per-pixel phase: the recorded median-buffer pairs (backward.cu:693-767, 773-804) ----
   if (GEO && inside && ent_n > 0) {
-    const float sumw = a.sum_w[pix_id];
+    // per-pixel constants of the valid source views: independent loads, all in flight together
+    int sidx[MAX_SRC];
+#pragma unroll
+    for (int mm = 0; mm < MAX_SRC; mm++) sidx[mm] = a.valid_idx[mm * HW + pix_id];
+    const float inv_sumw = __fdividef(1.f, a.sum_w[pix_id]);
     const float depth_pix = a.depth_pixels[pix_id];
+    int nvalid = MAX_SRC;
+#pragma unroll
+    for (int mm = MAX_SRC - 1; mm >= 0; mm--)
+      if (sidx[mm] == -1) nvalid = mm;   // slots past the terminator are uninitialised and never used
+    float inv_vw[MAX_SRC], dLw[MAX_SRC][3], wpix[MAX_SRC][3];
+#pragma unroll
+    for (int mm = 0; mm < MAX_SRC; mm++) {
+      if (mm < nvalid) {
+        inv_vw[mm] = __fdividef(1.f, a.valid_w[mm * HW + pix_id]);
+#pragma unroll
+        for (int n_i = 0; n_i < 3; n_i++) {
+          dLw[mm][n_i] = a.dL_dwarped[mm * 3 * HW + n_i * HW + pix_id];
+          wpix[mm][n_i] = a.warped_pixels[mm * 3 * HW + n_i * HW + pix_id];
+        }
+      }
+    }
+    const float A_val = (pixf.x - cx) / fx;
+    const float B_val = (pixf.y - cy) / fy;
 #pragma unroll 1
     for (int e = 0; e < ent_n; e++) {
       uint32_t gid = 0;
@@ -391,48 +416,47 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
           -distance_gauss / (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
       const float3 ip = {(pixf.x - cx) * intersected_depth / fx, (pixf.y - cy) * intersected_depth / fy,
                          intersected_depth};
-      float dL_dz = dL_ddepth * dchannel_dcolor / sumw;
-      dL_dalpha += dL_ddepth * (intersected_depth - depth_pix) / sumw;
-      for (int mm = 0; mm < MAX_SRC; mm++) {
-        const int src_idx = a.valid_idx[mm * HW + pix_id];
-        if (src_idx == -1) break;
-        const float* r2s = &s_ref_to_src[src_idx * 16];
-        const float3 tp = {r2s[0] * ip.x + r2s[1] * ip.y + r2s[2] * ip.z + r2s[3],
-                           r2s[4] * ip.x + r2s[5] * ip.y + r2s[6] * ip.z + r2s[7],
-                           r2s[8] * ip.x + r2s[9] * ip.y + r2s[10] * ip.z + r2s[11]};
-        const float2 pp = {(tp.x * fx / tp.z) + cx, (tp.y * fy / tp.z) + cy};
-        if (pp.x >= 0 && pp.x <= W - 1 && pp.y >= 0 && pp.y <= H - 1) {
-          const float4 texC = tex2DLayered<float4>(a.texColor, pp.x + 0.5f, pp.y + 0.5f, src_idx);
-          const float wc[3] = {texC.x, texC.y, texC.z};
-          const float vw = a.valid_w[mm * HW + pix_id];
-          float dLc[3];
+      float dL_dz = dL_ddepth * dchannel_dcolor * inv_sumw;
+      dL_dalpha += dL_ddepth * (intersected_depth - depth_pix) * inv_sumw;
 #pragma unroll
-          for (int n_i = 0; n_i < 3; n_i++) {
-            const float dLw = a.dL_dwarped[mm * 3 * HW + n_i * HW + pix_id];
-            dLc[n_i] = dLw * dchannel_dcolor / vw;
-            dL_dalpha += dLw * (wc[n_i] - a.warped_pixels[mm * 3 * HW + n_i * HW + pix_id]) / vw;
+      for (int mm = 0; mm < MAX_SRC; mm++) {
+        if (mm < nvalid) {
+          const int src_idx = sidx[mm];
+          const float* r2s = &s_ref_to_src[src_idx * 16];
+          const float3 tp = {r2s[0] * ip.x + r2s[1] * ip.y + r2s[2] * ip.z + r2s[3],
+                             r2s[4] * ip.x + r2s[5] * ip.y + r2s[6] * ip.z + r2s[7],
+                             r2s[8] * ip.x + r2s[9] * ip.y + r2s[10] * ip.z + r2s[11]};
+          const float2 pp = {(tp.x * fx / tp.z) + cx, (tp.y * fy / tp.z) + cy};
+          if (pp.x >= 0 && pp.x <= W - 1 && pp.y >= 0 && pp.y <= H - 1) {
+            const float4 texC = tex2DLayered<float4>(a.texColor, pp.x + 0.5f, pp.y + 0.5f, src_idx);
+            const float wc[3] = {texC.x, texC.y, texC.z};
+            float dLc[3];
+#pragma unroll
+            for (int n_i = 0; n_i < 3; n_i++) {
+              dLc[n_i] = dLw[mm][n_i] * dchannel_dcolor * inv_vw[mm];
+              dL_dalpha += dLw[mm][n_i] * (wc[n_i] - wpix[mm][n_i]) * inv_vw[mm];
+            }
+            const float U = r2s[0] * A_val + r2s[1] * B_val + r2s[2];
+            const float V = r2s[4] * A_val + r2s[5] * B_val + r2s[6];
+            const float W_coeff = r2s[8] * A_val + r2s[9] * B_val + r2s[10];
+            const float r0 = r2s[3], r1 = r2s[7], r2 = r2s[11];
+            const float denom = (W_coeff * intersected_depth + r2);
+            const float inv_d2 = __fdividef(1.f, denom * denom);
+            const float dp_x_dd = fx * (U * r2 - W_coeff * r0) * inv_d2;
+            const float dp_y_dd = fy * (V * r2 - W_coeff * r1) * inv_d2;
+            const float2 dpp = bilinearInterpolateBackward(src_idx, a.texColor, pp, make_float3(dLc[0], dLc[1], dLc[2]));
+            const float from_color = dpp.x * dp_x_dd + dpp.y * dp_y_dd;
+            dL_dz += from_color;
+            // accumulated inside the view loop, exactly like backward.cu:757-763
+            dL_dall_map_temp[4] += (-dL_dz / tmp_gauss);
+            dL_dall_map_temp[0] += dL_dz * tmp_gauss2 * ray.x;
+            dL_dall_map_temp[1] += dL_dz * tmp_gauss2 * ray.y;
+            dL_dall_map_temp[2] += dL_dz * tmp_gauss2;
           }
-          const float A_val = (pixf.x - cx) / fx;
-          const float B_val = (pixf.y - cy) / fy;
-          const float U = r2s[0] * A_val + r2s[1] * B_val + r2s[2];
-          const float V = r2s[4] * A_val + r2s[5] * B_val + r2s[6];
-          const float W_coeff = r2s[8] * A_val + r2s[9] * B_val + r2s[10];
-          const float r0 = r2s[3], r1 = r2s[7], r2 = r2s[11];
-          const float denom = (W_coeff * intersected_depth + r2);
-          const float dp_x_dd = fx * (U * r2 - W_coeff * r0) / (denom * denom);
-          const float dp_y_dd = fy * (V * r2 - W_coeff * r1) / (denom * denom);
-          const float2 dpp = bilinearInterpolateBackward(src_idx, a.texColor, pp, make_float3(dLc[0], dLc[1], dLc[2]));
-          const float from_color = dpp.x * dp_x_dd + dpp.y * dp_y_dd;
-          dL_dz += from_color;
-          // accumulated inside the view loop, exactly like backward.cu:757-763
-          dL_dall_map_temp[4] += (-dL_dz / tmp_gauss);
-          dL_dall_map_temp[0] += dL_dz * tmp_gauss2 * ray.x;
-          dL_dall_map_temp[1] += dL_dz * tmp_gauss2 * ray.y;
-          dL_dall_map_temp[2] += dL_dz * tmp_gauss2;
         }
       }
       dL_dalpha *= Te;
-      dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+      dL_dalpha += (-T_final * __fdividef(1.f, 1.f - alpha)) * bg_dot_dpixel;
       const float dL_dG = g1.y * dL_dalpha;
       const float gdx = G * d.x;
       const float gdy = G * d.y;

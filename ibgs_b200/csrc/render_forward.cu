@@ -70,7 +70,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 template <int MODE, int BL>
-__global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
+__global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a) {
   constexpr int BEFORE = (BL + 1) / 2;  // forward.cu:384
   constexpr int BELOW = BL - BEFORE;    // forward.cu:385
   constexpr unsigned FULL = 0xffffffffu;
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
   uint32_t last_contributor = 0;
   float C[3] = {0.f, 0.f, 0.f};
   float normal_accum[3] = {0.f, 0.f, 0.f};
-  float zb[BL], wb[BL];
+  float zb[BL], wb[BL], db[BL];   // GEO: zb = depth denominator, db = plane distance; DEPTH: zb = depth
   uint32_t cb[BL];
 #pragma unroll
-  for (int k = 0; k < BL; k++) { zb[k] = 0.f; wb[k] = 0.f; cb[k] = 0u; }
+  for (int k = 0; k < BL; k++) { zb[k] = 0.f; wb[k] = 0.f; db[k] = 0.f; cb[k] = 0u; }
   int before_ptr = 0;
   int below_count = 0;
   float total_buffer_weight = 0.0f;
@@ -192,28 +192,36 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
         }
         if (MODE != MODE_COLOR) {
           const float4 g3 = wrec[buf][3][b];
-          // forward.cu:439-442
-          const float intersected_depth = -g2.w / (g3.x * ray.x + g3.y * ray.y + g3.z + epsilon);
+          // forward.cu:439-442: intersected_depth = -d / (n.ray + eps)
+          const float z_den = g3.x * ray.x + g3.y * ray.y + g3.z + epsilon;
           if (MODE == MODE_GEO) {
             normal_accum[0] += g3.x * aT;
             normal_accum[1] += g3.y * aT;
             normal_accum[2] += g3.z * aT;
-            if (intersected_depth > 0.0f) {
+            // The ring only ever needs the depths of the entries it still holds at the end, so the IEEE
+            // division is postponed to the epilogue: the ring stores the denominator (the numerator -d is
+            // re-read there).  "depth > 0" is decided from the operand signs: -d/den > 0 <=> d and den are
+            // non-zero with opposite signs (den = 0 gives +-inf of the wrong sign or NaN, NaN compares false;
+            // the quotient cannot underflow to 0 for finite plane parameters and a ray inside the frustum).
+            const bool need = (T > 0.5f) || (below_count < BELOW);
+            const bool z_pos = (g2.w > 0.0f && z_den < 0.0f) || (g2.w < 0.0f && z_den > 0.0f);
+            if (need && z_pos) {
               if (T > 0.5f) {
 #pragma unroll
                 for (int k = 0; k < BEFORE; k++)
-                  if (before_ptr == k) { zb[k] = intersected_depth; wb[k] = aT; cb[k] = contributor; }
+                  if (before_ptr == k) { zb[k] = z_den; db[k] = g2.w; wb[k] = aT; cb[k] = contributor; }
                 before_ptr = (before_ptr + 1) % BEFORE;
-              } else if (below_count < BELOW) {
+              } else {
 #pragma unroll
                 for (int k = 0; k < BELOW; k++)
                   if (below_count == k) {
-                    zb[BEFORE + k] = intersected_depth; wb[BEFORE + k] = aT; cb[BEFORE + k] = contributor;
+                    zb[BEFORE + k] = z_den; db[BEFORE + k] = g2.w; wb[BEFORE + k] = aT; cb[BEFORE + k] = contributor;
                   }
                 below_count++;
               }
             }
           } else {  // MODE_DEPTH, forward.cu:466-489
+            const float intersected_depth = -g2.w / z_den;
             if (intersected_depth > 0.0f) {
               if (T > 0.5f) {
                 float old_w = 0.f, old_z = 0.f;
@@ -283,7 +291,7 @@ __global__ void __launch_bounds__(256) render_forward_kernel(const FwdArgs a) {
     for (int i = 0; i < BL; i++) {
       const float weight = wb[i];
       if (weight != 0.0f) {
-        const float idepth = zb[i];
+        const float idepth = -db[i] / zb[i];  // the postponed forward.cu:439-442 division, same operands
         const float3 ipt = {pix_diff_x * idepth * inv_focal_x, pix_diff_y * idepth * inv_focal_y, idepth};
 #pragma unroll
         for (int s = 0; s < MAX_SRC; s++) {

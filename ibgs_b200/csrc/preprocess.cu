@@ -205,16 +205,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
 
   const float opacity = a.opacities[idx];
 
-  // Conservative extent of {alpha >= 1/255}: o*exp(power) >= 1/255  <=>  -power <= ln(255 o) =: tau, and
-  // {0.5 d^T Conic d <= tau} has the axis-aligned half-extents sqrt(2 tau cov_xx), sqrt(2 tau cov_yy).
-  // The renderers use it ONLY to skip pairs the reference would reject at forward.cu:425; a margin
-  // covers __expf / rounding error.  NaN never culls (comparisons false).
-  float tau = __logf(255.0f * opacity) + 0.02f;
-  float hx = -1.0f, hy = -1.0f;
-  if (!(tau < 0.0f)) {
-    hx = sqrtf(2.0f * tau * cov.x) * 1.0005f + 0.02f;
-    hy = sqrtf(2.0f * tau * cov.z) * 1.0005f + 0.02f;
-  }
+  // Cull threshold for the tile renderers: o*exp(power) >= 1/255  <=>  -power <= ln(255 o) =: tau.  A sub-tile
+  // whose minimum of -power exceeds tau cannot blend this Gaussian (the reference would reject every pair at
+  // forward.cu:425); the 0.02 margin covers __expf / rounding error.  NaN never culls (comparisons false).
+  const float tau = __logf(255.0f * opacity) + 0.02f;
 
   float4 plane_n = {0.f, 0.f, 0.f, 0.f};
   float plane_d = 0.f;
@@ -229,7 +223,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
   a.radii[idx] = my_radius;
   float4* rec = a.rec + 4 * (size_t)idx;
   rec[0] = {point_image.x, point_image.y, conic.x, conic.y};
-  rec[1] = {conic.z, opacity, hx, hy};
+  rec[1] = {conic.z, opacity, tau, 0.f};
   rec[2] = {feat.x, feat.y, feat.z, plane_d};
   rec[3] = plane_n;
   a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);

@@ -162,9 +162,7 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
       if (j < total) {
         const float4 q0 = wrec[buf][0][lane];
         const float4 q1 = wrec[buf][1][lane];
-        const float ddx = fmaxf(fmaxf(wx0 - q0.x, q0.x - wx1), 0.0f);
-        const float ddy = fmaxf(fmaxf(wy0 - q0.y, q0.y - wy1), 0.0f);
-        keep = !(ddx > q1.z || ddy > q1.w);
+        keep = subtile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, wx0, wx1, wy0, wy1);
       }
       unsigned m = __ballot_sync(FULL, keep);
       while (m) {

@@ -105,7 +105,7 @@ def decode_ours(state):
     go, _ = N.state_layout(N.IBGS_BUF_GEOM, P)
     rec = view(g, go[0], 16 * P, torch.float32).view(P, 16)
     out = dict(
-        means2D=rec[:, 0:2], conic_opacity=torch.cat([rec[:, 2:5], rec[:, 5:6]], dim=1), cull=rec[:, 6:8],
+        means2D=rec[:, 0:2], conic_opacity=torch.cat([rec[:, 2:5], rec[:, 5:6]], dim=1), cull_tau=rec[:, 6],
         rgb=rec[:, 8:11], plane_d=rec[:, 11], plane_n=rec[:, 12:15],
         depths=view(g, go[1], P, torch.float32), tiles_touched=view(g, go[2], P, torch.int32),
         point_offsets=view(g, go[3], P, torch.int32), clamped=view(g, go[4], P, torch.uint8))

@@ -29,7 +29,7 @@ ProfPair g_prof_open[PROF_COUNT];
 bool g_prof_is_open[PROF_COUNT] = {false};
 double g_prof_ms[PROF_COUNT] = {0};
 long long g_prof_n[PROF_COUNT] = {0};
-const char* g_prof_names[PROF_COUNT] = {"preprocess", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
+const char* g_prof_names[PROF_COUNT] = {"preprocess", "depth_order_sort", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
                                         "texture_fill", "render_forward", "render_backward", "preprocess_backward"};
 void prof_drain() {
   for (auto& p : g_prof_pending) {
@@ -132,7 +132,7 @@ extern "C" int ibgs_state_layout(int which, size_t count, size_t aux, size_t* of
   if (which == IBGS_BUF_GEOM) {
     GeomState g;
     total = carve_geom(g, base, count);
-    offs = {(size_t)g.rec, (size_t)g.depths, (size_t)g.tiles_touched, (size_t)g.point_offsets, (size_t)g.clamped};
+    offs = {(size_t)g.rec, (size_t)g.depths, (size_t)g.tiles_touched, (size_t)g.clamped};
   } else if (which == IBGS_BUF_IMAGE) {
     ImageState s;
     total = carve_image(s, base, count, aux);
@@ -143,11 +143,10 @@ extern "C" int ibgs_state_layout(int which, size_t count, size_t aux, size_t* of
     total = carve_binning(b, base, count);
     offs = {(size_t)b.point_list};
   } else if (which == IBGS_BUF_SCRATCH) {
-    // the (second) forward scratch request: binning temporaries for R=count instances
-    (void)aux;
+    // the (second) forward scratch request: binning temporaries for R=count instances, aux = number of tiles
     ScratchState sc;
-    total = carve_scratch(sc, base, count, 64);
-    offs = {(size_t)sc.keys_unsorted, (size_t)sc.keys_sorted, (size_t)sc.vals_unsorted, (size_t)sc.sort_temp};
+    total = carve_scratch(sc, base, count, ibgs_sort_bits((int32_t)(aux ? aux : 1)) - 32);
+    offs = {(size_t)sc.tiles_unsorted, (size_t)sc.tiles_sorted, (size_t)sc.vals_unsorted, (size_t)sc.sort_temp};
   } else {
     ibgs_set_error("unknown buffer id %d", which);
     return IBGS_EINVAL;
@@ -207,19 +206,21 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
     if (rc != IBGS_OK) return rc;
   }
 
-  rc = launch_preprocess(*a, g, focal_x, focal_y, grid, s);
-  if (rc != IBGS_OK) return rc;
-
-  // scan needs a little temp space: take it from a first scratch request sized for the scan only
-  const size_t scan_bytes = align_up(scan_temp_bytes((size_t)P), 256);
   if (!g_pinned_count) CUDA_TRY(cudaHostAlloc((void**)&g_pinned_count, 64, cudaHostAllocDefault));
 
-  // We do not know R yet; ask for the scan temp now, and for the binning scratch once R is known.
-  char* scan_temp = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, scan_bytes);
-  if (!scan_temp) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
-  rc = run_scan(g, (size_t)P, scan_temp, scan_bytes, s);
+  // We do not know R yet: the first scratch request holds the P-sized depth-order state, the second one (once R
+  // is known) the R-sized binning temporaries.  Both stay alive until the forward's last launch is enqueued.
+  OrderState ord;
+  const size_t order_bytes = carve_order(ord, nullptr, (size_t)P);
+  char* order_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, order_bytes);
+  if (!order_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  carve_order(ord, order_base, (size_t)P);
+
+  rc = launch_preprocess(*a, g, ord.iota, focal_x, focal_y, grid, s);
   if (rc != IBGS_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(g_pinned_count, g.point_offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  rc = run_depth_order(g, ord, (size_t)P, s);
+  if (rc != IBGS_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g_pinned_count, ord.offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   const uint32_t R_u = *(volatile uint32_t*)g_pinned_count;
   if (R_u > 0x7fffffffu) {
@@ -236,11 +237,10 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
   carve_binning(b, bin_base, (size_t)R);
 
   ScratchState sc;
-  size_t scratch_bytes = carve_scratch(sc, nullptr, (size_t)R, ibgs_sort_bits((int32_t)T));
-  // second scratch request replaces the first (the caller may free the scan temp, stream-ordered)
+  size_t scratch_bytes = carve_scratch(sc, nullptr, (size_t)R, ibgs_sort_bits((int32_t)T) - 32);
   char* scratch_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, scratch_bytes);
   if (!scratch_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
-  rc = run_binning(*a, g, im, scratch_base, scratch_bytes, b, R, grid, s);
+  rc = run_binning(*a, g, ord, im, scratch_base, scratch_bytes, b, R, grid, s);
   if (rc != IBGS_OK) return rc;
 
   rc = launch_render_forward(*a, g, im, b, tex, focal_x, focal_y, grid, s);
@@ -285,9 +285,12 @@ extern "C" int ibgs_backward(IbgsBackwardArgs* a, void* stream_v) {
   carve_image(im, (char*)a->image_buffer, N, T);
   carve_binning(b, (char*)a->binning_buffer, (size_t)a->R);
 
-  const size_t arena_bytes = (size_t)P * 64;
-  float4* arena = (float4*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, arena_bytes);
+  // one scratch request: [P][16] accumulation arena (zeroed) | per-pixel median-pair lists (render_geo only)
+  const size_t arena_bytes = align_up((size_t)P * 64, 256);
+  const size_t ent_bytes = render_backward_scratch_bytes(N, v.buffer_length, v.render_geo);
+  float4* arena = (float4*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, arena_bytes + ent_bytes);
   if (!arena) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  void* ent_scratch = ent_bytes ? (void*)((char*)arena + arena_bytes) : nullptr;
   CUDA_TRY(cudaMemsetAsync(arena, 0, arena_bytes, s));
   COUNT_LAUNCH();
 
@@ -298,7 +301,7 @@ extern "C" int ibgs_backward(IbgsBackwardArgs* a, void* stream_v) {
                           a->tex_generation);
     if (rc != IBGS_OK) return rc;
   }
-  rc = launch_render_backward(*a, g, im, b, tex, focal_x, focal_y, grid, arena, s);
+  rc = launch_render_backward(*a, g, im, b, tex, focal_x, focal_y, grid, arena, ent_scratch, s);
   if (rc != IBGS_OK) return rc;
   rc = launch_preprocess_backward(*a, g, arena, focal_x, focal_y, s);
   return rc;

@@ -1,57 +1,68 @@
-// binning.cu -- tile binning: offsets scan, key/value duplication, 64-bit tile|depth sort, tile ranges.
+// binning.cu -- tile binning: depth order of the Gaussians, offsets scan, tile-instance emission, tile sort, ranges.
 //
 // Reference behaviour: cub::DeviceScan::InclusiveSum (rasterizer_impl.cu:426), duplicateWithKeys
-// (:187-228), getHigherMsb (:152-167), cub::DeviceRadixSort::SortPairs on bits [0, 32+msb) (:452-457),
-// cudaMemset + identifyTileRanges (:459-467, :233-255).  Integer path: results are bit-exact by
-// construction (same emission order, stable sort over the same bit range).
+// (:187-228), getHigherMsb (:152-167), cub::DeviceRadixSort::SortPairs of (tile<<32 | depth bits, Gaussian id)
+// on bits [0, 32+msb) (:452-457), cudaMemset + identifyTileRanges (:459-467, :233-255).  Its result -- the list
+// `point_list` ordered by tile, then by depth bits, ties by Gaussian id (stable sort, Gaussian-major emission)
+// -- and the tile ranges are what every later stage consumes; they are reproduced here bit for bit.
 //
-// The scan and the LSD radix sort are CCCL/CUB device primitives (library code, like the reference);
-// duplication and range identification are this project's kernels: duplication is warp-cooperative
-// so the 12 B/instance stores of one Gaussian's tile rectangle are issued by adjacent lanes instead of
-// one thread walking the rectangle serially.
+// How (this project's own decomposition; the radix sorts and the scan are CCCL/CUB device primitives, library
+// code like in the reference).  A 64-bit LSD sort of all R instances is 6 passes over 24-byte pairs at R = 15 M.
+// The depth half of the key is a property of the GAUSSIAN, not of the instance, so it is sorted once per
+// Gaussian instead of once per instance:
+//   1. stable sort of the P Gaussians by depth bits (32-bit keys, P << R items); culled Gaussians carry the key
+//      0xFFFFFFFF and land behind every visible one;
+//   2. inclusive scan of tiles_touched in that order -> write offsets;
+//   3. emission in depth order: instance = (tile id u32, Gaussian id u32), warp-cooperative for big rectangles;
+//   4. stable sort of the R instances by tile id only: ceil(msb(T)/8) = 2 passes over 8-byte pairs;
+//   5. tile ranges from the sorted tile ids.
+// Stability of (4) keeps each tile's instances in emission order = ascending depth bits, ties in ascending
+// Gaussian id (stability of (1)) -- exactly the reference's order.  The reference's sorted 64-bit keys are
+// (tile id << 32 | depth bits of point_list[i]); tests rebuild them from this state and compare bit-exactly.
 #include "common.cuh"
 #include <cub/cub.cuh>
 
 namespace {
 
-// one warp per 32 Gaussians; rectangles with >= 8 tiles are written cooperatively by the whole warp
-__global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int P, const float4* __restrict__ rec,
-                                                                  const float* __restrict__ depths,
-                                                                  const uint32_t* __restrict__ offsets,
-                                                                  uint64_t* __restrict__ keys,
-                                                                  uint32_t* __restrict__ vals,
-                                                                  const int* __restrict__ radii, dim3 grid) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+struct GatherTiles {
+  const uint32_t* tiles;
+  __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& g) const { return tiles[g]; }
+};
+
+// One thread per position in depth order; one warp per 32 positions; rectangles with >= 8 tiles are written
+// cooperatively by the whole warp.  Tile order inside a rectangle is row-major like rasterizer_impl.cu:215-226
+// (irrelevant for the result -- a Gaussian appears at most once per tile -- but kept).
+__global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ order,
+                                                             const uint32_t* __restrict__ tiles_touched,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const float4* __restrict__ rec,
+                                                             const int* __restrict__ radii,
+                                                             uint32_t* __restrict__ tile_ids,
+                                                             uint32_t* __restrict__ vals, dim3 grid) {
+  const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  int radius = 0;
-  uint32_t off = 0;
+  uint32_t gid = 0, n = 0, off = 0;
   uint2 rmin = {0, 0}, rmax = {0, 0};
-  uint32_t dbits = 0;
-  if (idx < P) radius = radii[idx];
-  if (radius > 0) {
-    off = (idx == 0) ? 0 : offsets[idx - 1];
-    float4 q0 = rec[4 * (size_t)idx];
-    getRect(make_float2(q0.x, q0.y), radius, rmin, rmax, grid);
-    dbits = __float_as_uint(depths[idx]);
+  if (pos < P) {
+    gid = order[pos];
+    n = tiles_touched[gid];
+  }
+  if (n > 0) {
+    off = (pos == 0) ? 0 : offsets[pos - 1];
+    const float4 q0 = rec[4 * (size_t)gid];
+    getRect(make_float2(q0.x, q0.y), radii[gid], rmin, rmax, grid);
   }
   const uint32_t w = rmax.x - rmin.x;
-  const uint32_t n = (radius > 0) ? w * (rmax.y - rmin.y) : 0;
-
-  // small rectangles: the owning lane writes them itself (row-major y then x, rasterizer_impl.cu:215-226)
   const bool big = n >= 8;
   if (n > 0 && !big) {
     uint32_t o = off;
     for (uint32_t y = rmin.y; y < rmax.y; y++)
       for (uint32_t x = rmin.x; x < rmax.x; x++) {
-        uint64_t key = y * grid.x + x;
-        key <<= 32;
-        key |= dbits;
-        keys[o] = key;
-        vals[o] = idx;
+        tile_ids[o] = y * grid.x + x;
+        vals[o] = gid;
         o++;
       }
   }
-  // large rectangles: all 32 lanes share the work, coalesced stores
   unsigned mask = __ballot_sync(0xffffffffu, big);
   while (mask) {
     const int src = __ffs(mask) - 1;
@@ -61,29 +72,25 @@ __global__ void __launch_bounds__(256) duplicate_with_keys_kernel(int P, const f
     const uint32_t s_w = __shfl_sync(0xffffffffu, w, src);
     const uint32_t s_x0 = __shfl_sync(0xffffffffu, rmin.x, src);
     const uint32_t s_y0 = __shfl_sync(0xffffffffu, rmin.y, src);
-    const uint32_t s_d = __shfl_sync(0xffffffffu, dbits, src);
-    const uint32_t s_idx = __shfl_sync(0xffffffffu, (uint32_t)idx, src);
+    const uint32_t s_gid = __shfl_sync(0xffffffffu, gid, src);
     for (uint32_t k = lane; k < s_n; k += 32) {
       const uint32_t y = s_y0 + k / s_w;
       const uint32_t x = s_x0 + k % s_w;
-      uint64_t key = y * grid.x + x;
-      key <<= 32;
-      key |= s_d;
-      keys[s_off + k] = key;
-      vals[s_off + k] = s_idx;
+      tile_ids[s_off + k] = y * grid.x + x;
+      vals[s_off + k] = s_gid;
     }
   }
 }
 
-// reference rasterizer_impl.cu:233-255
-__global__ void identify_tile_ranges_kernel(int L, const uint64_t* __restrict__ keys, uint2* ranges) {
+// reference rasterizer_impl.cu:233-255 (on 32-bit tile ids instead of the high half of 64-bit keys)
+__global__ void identify_tile_ranges_kernel(int L, const uint32_t* __restrict__ tile_ids, uint2* ranges) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= L) return;
-  uint32_t currtile = keys[idx] >> 32;
+  uint32_t currtile = tile_ids[idx];
   if (idx == 0)
     ranges[currtile].x = 0;
   else {
-    uint32_t prevtile = keys[idx - 1] >> 32;
+    uint32_t prevtile = tile_ids[idx - 1];
     if (currtile != prevtile) {
       ranges[prevtile].y = idx;
       ranges[currtile].x = idx;
@@ -111,27 +118,51 @@ uint32_t getHigherMsb(uint32_t n) {
 
 extern "C" int ibgs_sort_bits(int32_t num_tiles) { return 32 + (int)getHigherMsb((uint32_t)num_tiles); }
 
-size_t scan_temp_bytes(size_t P) {
-  size_t bytes = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)P);
-  return bytes;
+size_t carve_order(OrderState& o, char* base, size_t P) {
+  size_t off = 0;
+  carve(off, o.iota, base, P);
+  carve(off, o.keys_sorted, base, P);
+  carve(off, o.order, base, P);
+  carve(off, o.offsets, base, P);
+  size_t sort_bytes = 0, scan_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)P, 0, 32);
+  cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t*> it((const uint32_t*)nullptr, GatherTiles{nullptr});
+  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (uint32_t*)nullptr, (int)P);
+  o.temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  off = align_up(off, 256);
+  o.temp = base + off;
+  off += o.temp_bytes;
+  return align_up(off, 256);
 }
 
-int run_scan(const GeomState& g, size_t P, void* temp, size_t temp_bytes, cudaStream_t s) {
-  ProfScope prof(PROF_SCAN, s);
-  CUDA_TRY(cub::DeviceScan::InclusiveSum(temp, temp_bytes, g.tiles_touched, g.point_offsets, (int)P, s));
-  g_launch_count += 2;
+// steps 1-2: depth order of the Gaussians + write offsets in that order
+int run_depth_order(const GeomState& g, const OrderState& o, size_t P, cudaStream_t s) {
+  {
+    ProfScope prof(PROF_GSORT, s);
+    size_t tb = o.temp_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(o.temp, tb, reinterpret_cast<const uint32_t*>(g.depths), o.keys_sorted,
+                                             o.iota, o.order, (int)P, 0, 32, s));
+    g_launch_count += 5;
+  }
+  {
+    ProfScope prof(PROF_SCAN, s);
+    size_t tb = o.temp_bytes;
+    cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t*> it(o.order, GatherTiles{g.tiles_touched});
+    CUDA_TRY(cub::DeviceScan::InclusiveSum(o.temp, tb, it, o.offsets, (int)P, s));
+    g_launch_count += 2;
+  }
   return IBGS_OK;
 }
 
-size_t carve_scratch(ScratchState& sc, char* base, size_t R, int end_bit) {
+size_t carve_scratch(ScratchState& sc, char* base, size_t R, int tile_bits) {
   size_t off = 0;
-  carve(off, sc.keys_unsorted, base, R);
-  carve(off, sc.keys_sorted, base, R);
+  carve(off, sc.tiles_unsorted, base, R);
+  carve(off, sc.tiles_sorted, base, R);
   carve(off, sc.vals_unsorted, base, R);
   size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint64_t*)nullptr, (uint64_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)R, 0, end_bit);
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)R, 0, tile_bits);
   sc.sort_temp_bytes = bytes;
   off = align_up(off, 256);
   sc.sort_temp = base + off;
@@ -139,35 +170,34 @@ size_t carve_scratch(ScratchState& sc, char* base, size_t R, int end_bit) {
   return align_up(off, 256);
 }
 
-int run_binning(const IbgsForwardArgs& a, const GeomState& g, const ImageState& im, char* scratch_base,
-                size_t scratch_bytes, BinningState& b, int64_t R, dim3 grid, cudaStream_t s) {
+// steps 3-5
+int run_binning(const IbgsForwardArgs& a, const GeomState& g, const OrderState& o, const ImageState& im,
+                char* scratch_base, size_t scratch_bytes, BinningState& b, int64_t R, dim3 grid, cudaStream_t s) {
   const int debug = a.view.debug;
-  const int end_bit = ibgs_sort_bits((int32_t)(grid.x * grid.y));
+  const int tile_bits = ibgs_sort_bits((int32_t)(grid.x * grid.y)) - 32;
   ScratchState sc;
-  size_t need = carve_scratch(sc, scratch_base, (size_t)R, end_bit);
+  size_t need = carve_scratch(sc, scratch_base, (size_t)R, tile_bits);
   if (need > scratch_bytes) {
     ibgs_set_error("scratch too small: %zu < %zu", scratch_bytes, need);
     return IBGS_EINVAL;
   }
   {
     ProfScope prof(PROF_DUPLICATE, s);
-    duplicate_with_keys_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, g.rec, g.depths, g.point_offsets,
-                                                                 sc.keys_unsorted, sc.vals_unsorted, a.radii,
-                                                                 grid);
+    emit_instances_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, o.order, g.tiles_touched, o.offsets, g.rec, a.radii,
+                                                            sc.tiles_unsorted, sc.vals_unsorted, grid);
     KERNEL_CHECK(debug, s);
   }
   if (R > 0) {
     ProfScope prof(PROF_SORT, s);
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(sc.sort_temp, sc.sort_temp_bytes, sc.keys_unsorted,
-                                             sc.keys_sorted, sc.vals_unsorted, b.point_list, (int)R, 0,
-                                             end_bit, s));
-    g_launch_count += (end_bit + 7) / 8 + 1;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(sc.sort_temp, sc.sort_temp_bytes, sc.tiles_unsorted, sc.tiles_sorted,
+                                             sc.vals_unsorted, b.point_list, (int)R, 0, tile_bits, s));
+    g_launch_count += (tile_bits + 7) / 8 + 1;
   }
   {
     ProfScope prof(PROF_RANGES, s);
     CUDA_TRY(cudaMemsetAsync(im.ranges, 0, (size_t)grid.x * grid.y * sizeof(uint2), s));
     if (R > 0) {
-      identify_tile_ranges_kernel<<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, sc.keys_sorted, im.ranges);
+      identify_tile_ranges_kernel<<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, sc.tiles_sorted, im.ranges);
       KERNEL_CHECK(debug, s);
     }
   }

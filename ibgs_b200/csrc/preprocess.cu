@@ -36,6 +36,7 @@ struct PreArgs {
   float* depths;
   uint32_t* tiles_touched;
   uint8_t* clamped;
+  uint32_t* iota;
   dim3 grid;
   int prefiltered;
   int render_depth_only;
@@ -149,6 +150,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
   // forward.cu:227-228
   a.radii[idx] = 0;
   a.tiles_touched[idx] = 0;
+  // binning.cu sorts the Gaussians by the bit pattern of depths[]: culled ones get the largest key
+  a.iota[idx] = idx;
+  reinterpret_cast<uint32_t*>(a.depths)[idx] = 0xFFFFFFFFu;
 
   // in_frustum, auxiliary.h:143-168
   float3 p_orig = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
@@ -240,8 +244,8 @@ __global__ void mark_visible_kernel(int P, const float* means3D, const float* vi
 
 }  // namespace
 
-int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, float focal_x, float focal_y, dim3 grid,
-                      cudaStream_t s) {
+int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, uint32_t* iota, float focal_x, float focal_y,
+                      dim3 grid, cudaStream_t s) {
   PreArgs a;
   a.P = f.P;
   a.D = f.view.sh_degree;
@@ -269,6 +273,7 @@ int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, float focal_
   a.depths = g.depths;
   a.tiles_touched = g.tiles_touched;
   a.clamped = g.clamped;
+  a.iota = iota;
   a.grid = grid;
   a.prefiltered = f.view.prefiltered;
   a.render_depth_only = f.view.render_depth_only;

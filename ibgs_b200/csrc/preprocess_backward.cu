@@ -26,6 +26,7 @@ struct PBArgs {
   const float* view;
   const float* proj;
   float h_x, h_y, tan_fovx, tan_fovy;
+  float half_w, half_h;
   const float* campos;
   const float4* arena;
   int has_all_map;
@@ -80,8 +81,12 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a
     write_zero_row(a, idx);
     return;
   }
-  const float4 a0 = a.arena[4 * (size_t)idx + 0];
-  const float4 a1 = a.arena[4 * (size_t)idx + 1];
+  // slots 0-6 arrive unscaled from the tile renderer (render_backward.cu): apply 0.5*W, 0.5*H
+  // (backward.cu:606-607) and the -0.5 of the conic terms (:799-801) once per Gaussian
+  float4 a0 = a.arena[4 * (size_t)idx + 0];
+  float4 a1 = a.arena[4 * (size_t)idx + 1];
+  a0.x *= a.half_w; a0.y *= a.half_h; a0.z *= a.half_w; a0.w *= a.half_h;
+  a1.x *= -0.5f; a1.y *= -0.5f; a1.z *= -0.5f;
   const float4 a2 = a.arena[4 * (size_t)idx + 2];
   const float4 a3 = a.arena[4 * (size_t)idx + 3];
 
@@ -373,6 +378,8 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.cov3D_precomp = f.cov3D_precomp;
   a.view = f.view.viewmatrix;
   a.proj = f.view.projmatrix;
+  a.half_w = (float)(0.5 * f.view.image_width);
+  a.half_h = (float)(0.5 * f.view.image_height);
   a.h_x = focal_x;
   a.h_y = focal_y;
   a.tan_fovx = f.view.tanfovx;

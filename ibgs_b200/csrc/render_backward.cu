@@ -14,15 +14,18 @@
 //     without being loaded;
 //   * each lane culls its own Gaussian (alpha extent vs sub-tile, contributor >= max n_contrib of the
 //     warp); only survivors are evaluated;
-//   * the 15 per-pair gradient terms are reduced across the 32 pixels of the warp with a value-splitting
-//     shuffle butterfly (16+8+4+2+1 = 31 shuffles for all 16 slots instead of 16x5) and 16 lanes then
-//     issue ONE red.global.add.f32 each into the Gaussian's 64-byte row of a [P][16] arena: one 64-byte
-//     reduction per (warp, surviving Gaussian) instead of 16 same-address atomics per (pixel, Gaussian);
+//   * the 15 per-pair gradient terms are reduced across the 32 pixels of the warp by transposing them through a
+//     conflict-free shared-memory tile (warp_reduce16_smem: 4 STS.128 + 16 LDS + 1 SHFL per Gaussian) and 16
+//     lanes then issue ONE red.global.add.f32 each into the Gaussian's 64-byte row of a [P][16] arena: one
+//     64-byte reduction per (warp, surviving Gaussian) instead of 16 same-address atomics per (pixel, Gaussian);
 //   * the median-buffer terms (backward.cu:693-767: texture taps, per-view loops, per-pixel loads) touch
 //     at most buffer_length pairs per pixel but sit in the middle of the reference's pair loop, where they
 //     diverge the warp.  Here the pair loop only RECORDS those pairs (Gaussian id, T, colour/normal part of
-//     dL/dalpha); their whole gradient is evaluated afterwards in a dense per-pixel phase (every lane busy
-//     with its own entries) and added with vector reductions.
+//     dL/dalpha) into a per-pixel list in global scratch; a SECOND kernel (render_backward_median_kernel, one
+//     thread per pixel, every lane busy with its own entries) evaluates their whole gradient and adds it with
+//     vector reductions.  Splitting the kernels keeps the 40-odd per-pixel registers of that phase out of the
+//     pair loop's register allocation (3 CTAs/SM instead of 2) and lets the texture-latency-bound phase run at
+//     its own, high occupancy.
 // Summation order differs from the reference (which is itself run-to-run nondeterministic); the
 // parity gate for gradients is relative L2 <= 1e-3.
 #include "common.cuh"
@@ -53,6 +56,10 @@ struct BwdArgs {
   const float* dL_ddepths;
   const float* dL_dwarped;
   float4* arena;  // [P][4]
+  // recorded median-buffer pairs: three slot-major [MAXE][N] planes (Gaussian id bits, T, colour+normal part of
+  // dL/dalpha) `ent_stride` floats apart; written by the pair loop, read back by the same thread in phase B
+  float* ent;
+  size_t ent_stride;
 };
 
 // reference backward.cu:55-109
@@ -84,47 +91,36 @@ __forceinline__ __device__ float2 bilinearInterpolateBackward(int src_idx, cudaT
   return make_float2(du, dv);
 }
 
-// Sum 16 per-lane values across the warp.  On return v[0] of lane L holds the warp total of slot
-// slot_of_lane(L); lanes 2k and 2k+1 hold the same slot.
-__forceinline__ __device__ void warp_reduce16(float (&v)[16], int lane) {
+// Warp reduction of 16 per-lane values through shared memory.
+// Every lane holds 16 partial gradient terms of ONE Gaussian (its own pixel's share); the warp needs the 16
+// column sums.  A shuffle butterfly costs 31 SHFL + 62 SEL + 31 FADD per Gaussian; transposing through shared
+// memory costs 4 STS.128 + 16 LDS + 16 FADD + 1 SHFL:
+//   * lane l stores its 16 values as row l of a [32][16] float tile (4 x STS.128).  The float4 column index is
+//     XOR-swizzled with (l>>1)&3 and rows 16..31 are shifted by one 16-float pad, which makes both the
+//     quarter-warp STS.128 phases and the scalar column reads below bank-conflict free;
+//   * lane (s = l&15, h = l>>4) then sums column s over rows 16h..16h+15 (16 scalar LDS: the two half-warps
+//     read rows of opposite parity -> disjoint bank halves; within a half the swizzle permutes 16 banks);
+//   * one xor-16 shuffle adds the two halves.  On return lanes 0..15 hold the total of slot `lane`.
+#define RED_ROW_FLOATS 16
+#define RED_WARP_FLOATS (33 * RED_ROW_FLOATS)
+__forceinline__ __device__ float warp_reduce16_smem(const float (&v)[16], float* red, int lane) {
   constexpr unsigned FULL = 0xffffffffu;
   {
-    const bool hi = lane & 16;
+    float4* row = reinterpret_cast<float4*>(red) + (lane * 4 + (lane >> 4) * 4);
+    const int cl = (lane >> 1) & 3;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-      const float send = hi ? v[i] : v[i + 8];
-      const float keep = hi ? v[i + 8] : v[i];
-      v[i] = keep + __shfl_xor_sync(FULL, send, 16);
-    }
+    for (int q = 0; q < 4; q++) row[q ^ cl] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
-  {
-    const bool hi = lane & 8;
+  __syncwarp();
+  const int s = lane & 15, h = lane >> 4;
+  const float* col = red + h * (16 * RED_ROW_FLOATS + RED_ROW_FLOATS) + (s & 3);
+  const int sq = s >> 2;
+  float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const float send = hi ? v[i] : v[i + 4];
-      const float keep = hi ? v[i + 4] : v[i];
-      v[i] = keep + __shfl_xor_sync(FULL, send, 8);
-    }
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const float send = hi ? v[i] : v[i + 2];
-      const float keep = hi ? v[i + 2] : v[i];
-      v[i] = keep + __shfl_xor_sync(FULL, send, 4);
-    }
-  }
-  {
-    const bool hi = lane & 2;
-    const float send = hi ? v[0] : v[1];
-    const float keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(FULL, send, 2);
-  }
-  v[0] += __shfl_xor_sync(FULL, v[0], 1);
-}
-__forceinline__ __device__ int slot_of_lane(int lane) {
-  return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+  for (int k = 0; k < 16; k++) sum += col[k * RED_ROW_FLOATS + ((sq ^ ((k >> 1) & 3)) << 2)];
+  sum += __shfl_xor_sync(FULL, sum, 16);
+  __syncwarp();  // all reads done before the next Gaussian's rows are stored
+  return sum;
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -139,13 +135,165 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // arena slots: 0,1 dmean2D.xy | 2,3 |dmean2D|.xy | 4,5,6 dconic x,y,w | 7 dopacity |
 //              8,9,10 dcolor | 11 dall_map[4] | 12,13,14 dall_map[0..2] | 15 unused
+// Slots 0-6 are accumulated UNSCALED: the per-view constants 0.5*W, 0.5*H (backward.cu:606-607,793-797) and the
+// -0.5 of the conic terms (:799-801) are applied once per Gaussian by preprocess_backward_kernel instead of once
+// per pixel-Gaussian pair here.
 // MAXE = number of median-buffer pairs a pixel can record (buffer_length + 1 spare for a pair that sits
-// exactly on the alpha threshold and is accepted by expf here but was rejected by __expf in the forward)
-template <bool GEO, int MAXE>
-__global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a) {
+// exactly on the alpha threshold and is decided differently than in the forward)
+
+// ---------------------------------------------------------------------------------------------------------
+// phase B: one recorded median-buffer pair of one pixel (backward.cu:693-767, 773-804).  Runs as the tail of the
+// pair kernel (every lane loops over its own pixel's list), so that its texture taps overlap with the ALU-bound
+// pair loops of the other warps on the SM.  Per-pixel values are loaded where they are used instead of being
+// kept in registers across the list: the pair loop's register budget (80 -> 3 CTAs/SM) must also hold for this.
+// ---------------------------------------------------------------------------------------------------------
+template <int NSRC>
+__device__ __forceinline__ void median_pair_backward(const BwdArgs& a, const float* s_ref_to_src, uint2 pix,
+                                                     uint32_t pix_id, int e) {
+  const int W = a.W, H = a.H;
+  const int HW = H * W;
+  const float* ent = a.ent + ((size_t)e * HW + pix_id);
+  const uint32_t gid = __float_as_uint(ent[0]);
+  const float Te = ent[a.ent_stride];
+  float dL_dalpha = ent[2 * a.ent_stride];
+  const float4* r = a.rec + 4 * (size_t)gid;
+  const float4 g0 = __ldg(r + 0), g1 = __ldg(r + 1), g2 = __ldg(r + 2), g3 = __ldg(r + 3);
+  int sidx[NSRC];
+#pragma unroll
+  for (int mm = 0; mm < NSRC; mm++) sidx[mm] = a.valid_idx[mm * HW + pix_id];
+  const float sum_w = a.sum_w[pix_id];
+  const float depth_pix = a.depth_pixels[pix_id];
+  const float dL_ddepth = a.dL_ddepths[pix_id];
+  const float T_final = a.final_T[pix_id];
+  float bg_dot_dpixel = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) bg_dot_dpixel += a.bg[i] * a.dL_dpixels[i * HW + pix_id];
+
+  const float2 pixf = {(float)pix.x, (float)pix.y};
+  const float fx = a.fx, fy = a.fy;
+  // backward.cu:545-547 (double on purpose: W*0.5 is a double expression there)
+  const float2 ray = {(float)((pixf.x - W * 0.5) / fx), (float)((pixf.y - H * 0.5) / fy)};
+  const float cx = float(W * 0.5f);
+  const float cy = float(H * 0.5f);
+  const float inv_sumw = __fdividef(1.f, sum_w);
+  // valid views are compacted into slots 0..nvalid-1, terminated by -1 when fewer than MAX_SRC (forward.cu:655);
+  // slots past the terminator are uninitialised and never used
+  int nvalid = NSRC;
+#pragma unroll
+  for (int mm = NSRC - 1; mm >= 0; mm--)
+    if (sidx[mm] == -1) nvalid = mm;
+  const float A_val = (pixf.x - cx) / fx;
+  const float B_val = (pixf.y - cy) / fy;
+
+  const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
+  const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
+  const float G = __expf(power);
+  const float alpha = min(0.99f, g1.y * G);
+  const float dchannel_dcolor = alpha * Te;
+  float dL_dall_map_temp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+
+  const float3 normal_gauss = {g3.x, g3.y, g3.z};
+  const float distance_gauss = g2.w;
+  const float tmp_gauss = (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
+  const float tmp_gauss2 = distance_gauss / (tmp_gauss * tmp_gauss);
+  const float intersected_depth =
+      -distance_gauss / (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
+  const float3 ip = {(pixf.x - cx) * intersected_depth / fx, (pixf.y - cy) * intersected_depth / fy,
+                     intersected_depth};
+  float dL_dz = dL_ddepth * dchannel_dcolor * inv_sumw;
+  dL_dalpha += dL_ddepth * (intersected_depth - depth_pix) * inv_sumw;
+  // The per-view bodies are written WITHOUT branches (dead / out-of-bounds views fetch texel (0,0) of layer 0 and
+  // their results are discarded with selects): one basic block lets the scheduler keep the loads and the five
+  // texture taps of several views in flight together -- this phase is bound by their latency.
+#pragma unroll
+  for (int mm = 0; mm < NSRC; mm++) {
+    const bool live = mm < nvalid;
+    const int src_idx = live ? sidx[mm] : 0;
+    const float* r2s = &s_ref_to_src[src_idx * 16];
+    const float3 tp = {r2s[0] * ip.x + r2s[1] * ip.y + r2s[2] * ip.z + r2s[3],
+                       r2s[4] * ip.x + r2s[5] * ip.y + r2s[6] * ip.z + r2s[7],
+                       r2s[8] * ip.x + r2s[9] * ip.y + r2s[10] * ip.z + r2s[11]};
+    float2 pp = {(tp.x * fx / tp.z) + cx, (tp.y * fy / tp.z) + cy};
+    const bool ok = live && (pp.x >= 0 && pp.x <= W - 1 && pp.y >= 0 && pp.y <= H - 1);  // NaN -> false
+    if (!ok) pp = make_float2(0.f, 0.f);
+    const float vw = a.valid_w[mm * HW + pix_id];
+    float dLw[3], wpix[3];
+#pragma unroll
+    for (int n_i = 0; n_i < 3; n_i++) {
+      dLw[n_i] = a.dL_dwarped[mm * 3 * HW + n_i * HW + pix_id];
+      wpix[n_i] = a.warped_pixels[mm * 3 * HW + n_i * HW + pix_id];
+    }
+    const float4 texC = tex2DLayered<float4>(a.texColor, pp.x + 0.5f, pp.y + 0.5f, src_idx);
+    const float inv_vw = __fdividef(1.f, vw);
+    const float wc[3] = {texC.x, texC.y, texC.z};
+    float dLc[3];
+    float alpha_term = 0.f;
+#pragma unroll
+    for (int n_i = 0; n_i < 3; n_i++) {
+      dLc[n_i] = dLw[n_i] * dchannel_dcolor * inv_vw;
+      alpha_term += dLw[n_i] * (wc[n_i] - wpix[n_i]) * inv_vw;
+    }
+    const float U = r2s[0] * A_val + r2s[1] * B_val + r2s[2];
+    const float V = r2s[4] * A_val + r2s[5] * B_val + r2s[6];
+    const float W_coeff = r2s[8] * A_val + r2s[9] * B_val + r2s[10];
+    const float r0 = r2s[3], r1 = r2s[7], r2 = r2s[11];
+    const float denom = (W_coeff * intersected_depth + r2);
+    const float inv_d2 = __fdividef(1.f, denom * denom);
+    const float dp_x_dd = fx * (U * r2 - W_coeff * r0) * inv_d2;
+    const float dp_y_dd = fy * (V * r2 - W_coeff * r1) * inv_d2;
+    const float2 dpp = bilinearInterpolateBackward(src_idx, a.texColor, pp, make_float3(dLc[0], dLc[1], dLc[2]));
+    const float from_color = dpp.x * dp_x_dd + dpp.y * dp_y_dd;
+    if (ok) {  // pure register arithmetic: compiles to selects
+      dL_dalpha += alpha_term;
+      dL_dz += from_color;
+      // accumulated inside the view loop, exactly like backward.cu:757-763
+      dL_dall_map_temp[4] += (-dL_dz / tmp_gauss);
+      dL_dall_map_temp[0] += dL_dz * tmp_gauss2 * ray.x;
+      dL_dall_map_temp[1] += dL_dz * tmp_gauss2 * ray.y;
+      dL_dall_map_temp[2] += dL_dz * tmp_gauss2;
+    }
+  }
+  dL_dalpha *= Te;
+  dL_dalpha += (-T_final * __fdividef(1.f, 1.f - alpha)) * bg_dot_dpixel;
+  // same UNSCALED slot convention as the pair loop (see there)
+  const float dL_dG = g1.y * dL_dalpha;
+  const float gdx = G * d.x;
+  const float gdy = G * d.y;
+  const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+  const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+  float4 f0, f1;
+  f0.x = dL_dG * dG_ddelx;
+  f0.y = dL_dG * dG_ddely;
+  f0.z = fabs(f0.x);
+  f0.w = fabs(f0.y);
+  const float hx = dL_dG * gdx, hy = dL_dG * gdy;
+  f1.x = hx * d.x;
+  f1.y = hx * d.y;
+  f1.z = hy * d.y;
+  f1.w = G * dL_dalpha;
+  float4* dst = a.arena + 4 * (size_t)gid;
+  atomicAdd(dst + 0, f0);
+  atomicAdd(dst + 1, f1);
+  if (dL_dall_map_temp[4] != 0.f || dL_dall_map_temp[0] != 0.f || dL_dall_map_temp[1] != 0.f ||
+      dL_dall_map_temp[2] != 0.f) {
+    atomicAdd(reinterpret_cast<float*>(a.arena) + 16 * (size_t)gid + 11, dL_dall_map_temp[4]);
+    atomicAdd(dst + 3, make_float4(dL_dall_map_temp[0], dL_dall_map_temp[1], dL_dall_map_temp[2], 0.f));
+  }
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel A: the pair loop
+// ---------------------------------------------------------------------------------------------------------
+template <bool GEO, int MAXE, int NSRC>
+__global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const BwdArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
-  __shared__ float4 s_rec[8][2][4][32];
-  __shared__ float s_ref_to_src[MAX_SRC * 16];
+  // dynamic shared memory (BWD_SMEM_BYTES): record double buffers | reduction tiles | source-view matrices
+  extern __shared__ float4 s_dyn[];
+  float4(*s_rec)[2][4][32] = reinterpret_cast<float4(*)[2][4][32]>(s_dyn);
+  float* s_red_all = reinterpret_cast<float*>(s_dyn + 8 * 2 * 4 * 32);
+  float* s_ref_to_src = s_red_all + 8 * RED_WARP_FLOATS;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -157,62 +305,64 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
   const uint2 pix = {(unsigned)(sub_x0 + (lane & 7)), (unsigned)(sub_y0 + (lane >> 3))};
   const uint32_t pix_id = W * pix.y + pix.x;
   const float2 pixf = {(float)pix.x, (float)pix.y};
-  const float fx = a.fx, fy = a.fy;
-  // backward.cu:545-547 (double on purpose: W*0.5 is a double expression there)
-  const float2 ray = {(float)((pixf.x - W * 0.5) / fx), (float)((pixf.y - H * 0.5) / fy)};
-  const float cx = float(W * 0.5f);
-  const float cy = float(H * 0.5f);
   const bool inside = pix.x < (unsigned)W && pix.y < (unsigned)H;
-
-  const float wx0 = (float)sub_x0, wx1 = (float)(sub_x0 + 7);
-  const float wy0 = (float)sub_y0, wy1 = (float)(sub_y0 + 3);
 
   const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
   const int total = (int)(range.y - range.x);
 
   if (GEO) {
     if (tid < a.nb_src * 16) s_ref_to_src[tid] = a.ref_to_src_list[tid];
-    __syncthreads();
+    __syncthreads();  // the only CTA barrier
   }
 
   const float T_final = inside ? a.final_T[pix_id] : 0;
   float T = T_final;
   const uint32_t last_contributor = inside ? a.n_contrib[pix_id] : 0;
-  const int min_median_contributor = (GEO && inside) ? (int)a.low[pix_id] : 0;
-  const int max_median_contributor = (GEO && inside) ? (int)a.high[pix_id] : 0;
+  // backward.cu:693 compares the unsigned contributor with (int) low-1 / high-1: same unsigned wrap here
+  const uint32_t median_lo = (GEO && inside) ? (uint32_t)((int)a.low[pix_id] - 1) : 1u;
+  const uint32_t median_hi = (GEO && inside) ? (uint32_t)((int)a.high[pix_id] - 1) : 0u;
   const uint32_t warp_max_contrib = __reduce_max_sync(FULL, last_contributor);
 
   float accum_rec[3] = {0.f, 0.f, 0.f};
   float accum_nrm[3] = {0.f, 0.f, 0.f};
   float dL_dpixel[3] = {0.f, 0.f, 0.f};
   float dL_dnormal[3] = {0.f, 0.f, 0.f};
-  float dL_ddepth = 0.f;
   if (inside) {
 #pragma unroll
     for (int i = 0; i < 3; i++) dL_dpixel[i] = a.dL_dpixels[i * HW + pix_id];
     if (GEO) {
 #pragma unroll
       for (int i = 0; i < 3; i++) dL_dnormal[i] = a.dL_dnormals[i * HW + pix_id];
-      dL_ddepth = a.dL_ddepths[pix_id];
     }
   }
   float bg_dot_dpixel = 0;  // backward.cu:779-781
 #pragma unroll
   for (int i = 0; i < 3; i++) bg_dot_dpixel += a.bg[i] * dL_dpixel[i];
-
-  float last_alpha = 0;
-  float last_color[3] = {0.f, 0.f, 0.f};
-  float last_nrm[3] = {0.f, 0.f, 0.f};
-  const float ddelx_dx = 0.5 * W;  // backward.cu:606-607
-  const float ddely_dy = 0.5 * H;
-
-  // recorded median-buffer pairs of this pixel
-  uint32_t ent_id[MAXE];
-  float ent_T[MAXE], ent_base[MAXE];
+  const float bgT = -T_final * bg_dot_dpixel;
+  if (GEO && inside) {
+    // phase B (after the pair loop) reads these per-pixel values with dependent loads: pull them into L2 now
+    prefetch_l2(a.sum_w + pix_id);
+    prefetch_l2(a.depth_pixels + pix_id);
+    prefetch_l2(a.dL_ddepths + pix_id);
+#pragma unroll
+    for (int mm = 0; mm < NSRC; mm++) {
+      prefetch_l2(a.valid_idx + mm * HW + pix_id);
+      prefetch_l2(a.valid_w + mm * HW + pix_id);
+#pragma unroll
+      for (int n_i = 0; n_i < 3; n_i++) {
+        prefetch_l2(a.dL_dwarped + (mm * 3 + n_i) * HW + pix_id);
+        prefetch_l2(a.warped_pixels + (mm * 3 + n_i) * HW + pix_id);
+      }
+    }
+  }
+  // the pair loop only needs the SIGN of the plane depth (recorded pairs are re-evaluated exactly, in the
+  // reference's double/float mix, by render_backward_median_kernel)
+  const float2 ray = {(pixf.x - 0.5f * (float)W) / a.fx, (pixf.y - 0.5f * (float)H) / a.fy};
   int ent_n = 0;
 
   float* arena_f = reinterpret_cast<float*>(a.arena);
   float4(*wrec)[4][32] = s_rec[warp];
+  float* wred = s_red_all + warp * RED_WARP_FLOATS;
 
   // list position p (0 = back of the list) holds contributor index total-1-p; positions with
   // contributor >= warp_max_contrib cannot contribute to any pixel of this warp: start after them
@@ -222,6 +372,8 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
   const uint32_t* plist_back = a.point_list + range.y - 1;  // plist_back[-p]
 
   if (c_begin < nchunks) {
+    const float wx0 = (float)sub_x0, wx1 = (float)(sub_x0 + 7);
+    const float wy0 = (float)sub_y0, wy1 = (float)(sub_y0 + 3);
     uint32_t id_next = 0u;  // id of this lane's Gaussian in the step being fetched
     {
       const int p = (c_begin << 5) + lane;
@@ -276,7 +428,10 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
         const float4 g1 = wrec[buf][1][b];
         const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
         const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
-        const float G = expf(power);  // precise exp here, __expf in the forward (backward.cu:648)
+        // The reference evaluates exp() here and __expf in the forward (backward.cu:648, forward.cu:424).  The fast
+        // one is used in both passes: same accept/reject decisions as our (and the reference's) forward, 2 ulp
+        // from exp() -- five orders of magnitude below the 1e-3 gradient gate.
+        const float G = __expf(power);
         const float alpha = min(0.99f, g1.y * G);
         const bool active = inside && !(contributor >= last_contributor) && !(power > 0.0f) &&
                             !(alpha < 1.0f / 255.0f);
@@ -290,20 +445,24 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
         if (active) {
           // 1/(1-alpha) once, approximate reciprocal (2 ulp): gradients are compared at 1e-3 relative L2 and
           // summed in a different order than the reference anyway
-          const float rinv = __fdividef(1.f, 1.f - alpha);
+          const float one_m_alpha = 1.f - alpha;
+          const float rinv = __fdividef(1.f, one_m_alpha);
           T = T * rinv;
           const float dchannel_dcolor = alpha * T;
           float dL_dalpha = 0.0f;
           const float4 g2 = wrec[buf][2][b];
           const float col[3] = {g2.x, g2.y, g2.z};
+          // accum_rec holds the blend of everything BEHIND this pair; the reference folds the previous pair in
+          // at the top of the next iteration (last_alpha / last_color, backward.cu:661-668) -- same values,
+          // folded here at the bottom of the current one instead, which frees seven registers
+          // (alpha*c + (1-alpha)*accum is evaluated as accum + alpha*(c - accum): the difference is needed anyway)
 #pragma unroll
           for (int ch = 0; ch < 3; ch++) {
-            const float c = col[ch];
-            accum_rec[ch] = last_alpha * last_color[ch] + (1.f - last_alpha) * accum_rec[ch];
-            last_color[ch] = c;
+            const float diff = col[ch] - accum_rec[ch];
             const float dL_dchannel = dL_dpixel[ch];
-            dL_dalpha += (c - accum_rec[ch]) * dL_dchannel;
+            dL_dalpha += diff * dL_dchannel;
             v[8 + ch] = dchannel_dcolor * dL_dchannel;
+            accum_rec[ch] += alpha * diff;
           }
           bool deferred = false;
           if (GEO) {
@@ -311,181 +470,79 @@ __global__ void __launch_bounds__(256, 2) render_backward_kernel(const BwdArgs a
             const float nrm[3] = {g3.x, g3.y, g3.z};
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-              const float c = nrm[ch];
-              accum_nrm[ch] = last_alpha * last_nrm[ch] + (1.f - last_alpha) * accum_nrm[ch];
-              last_nrm[ch] = c;
+              const float diff = nrm[ch] - accum_nrm[ch];
               const float dL_dchannel = dL_dnormal[ch];
-              dL_dalpha += (c - accum_nrm[ch]) * dL_dchannel;
+              dL_dalpha += diff * dL_dchannel;
               v[12 + ch] = dchannel_dcolor * dL_dchannel;
+              accum_nrm[ch] += alpha * diff;
             }
-            // median buffer, backward.cu:693-701 (unsigned comparison against int-1 as in the reference):
-            // a pair in range with a valid plane depth is only RECORDED here; see the dense phase below
-            if ((contributor >= (uint32_t)(min_median_contributor - 1)) &&
-                (contributor <= (uint32_t)(max_median_contributor - 1))) {
-              const float intersected_depth = -g2.w / (g3.x * ray.x + g3.y * ray.y + g3.z + 1.0e-8);
-              if (intersected_depth > 0.0f && ent_n < MAXE) {
-#pragma unroll
-                for (int k = 0; k < MAXE; k++)
-                  if (ent_n == k) { ent_id[k] = gid; ent_T[k] = T; ent_base[k] = dL_dalpha; }
+            // median buffer, backward.cu:693-701: a pair in range with a valid plane depth is only RECORDED
+            // here (Gaussian id, T, colour+normal part of dL/dalpha); render_backward_median_kernel does the rest
+            if (contributor >= median_lo && contributor <= median_hi) {
+              // intersected_depth = -d / (n.ray + 1e-8) > 0  <=>  d and the denominator have opposite signs
+              const float z_den = g3.x * ray.x + g3.y * ray.y + g3.z + 1.0e-8f;
+              const bool z_pos = (g2.w > 0.0f && z_den < 0.0f) || (g2.w < 0.0f && z_den > 0.0f);
+              if (z_pos && ent_n < MAXE) {
+                float* e = a.ent + ((size_t)ent_n * HW + pix_id);
+                e[0] = __uint_as_float(gid);
+                e[a.ent_stride] = T;
+                e[2 * a.ent_stride] = dL_dalpha;
                 ent_n++;
                 deferred = true;
               }
             }
           }
-          last_alpha = alpha;
           if (!deferred) {
             dL_dalpha *= T;
-            dL_dalpha += (-T_final * rinv) * bg_dot_dpixel;
+            dL_dalpha += bgT * rinv;
             const float dL_dG = g1.y * dL_dalpha;
             const float gdx = G * d.x;
             const float gdy = G * d.y;
             const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
             const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-            v[0] = dL_dG * dG_ddelx * ddelx_dx;
-            v[1] = dL_dG * dG_ddely * ddely_dy;
-            v[2] = fabs(dL_dG * dG_ddelx * ddelx_dx);
-            v[3] = fabs(dL_dG * dG_ddely * ddely_dy);
-            v[4] = -0.5f * gdx * d.x * dL_dG;
-            v[5] = -0.5f * gdx * d.y * dL_dG;
-            v[6] = -0.5f * gdy * d.y * dL_dG;
+            v[0] = dL_dG * dG_ddelx;
+            v[1] = dL_dG * dG_ddely;
+            v[2] = fabs(v[0]);
+            v[3] = fabs(v[1]);
+            const float hx = dL_dG * gdx, hy = dL_dG * gdy;
+            v[4] = hx * d.x;
+            v[5] = hx * d.y;
+            v[6] = hy * d.y;
             v[7] = G * dL_dalpha;
           }
         }
 
-        warp_reduce16(v, lane);
-        if ((lane & 1) == 0) {
-          const int slot = slot_of_lane(lane);
-          if (GEO ? (slot != 11 && slot != 15) : (slot < 11)) atomicAdd(arena_f + 16 * (size_t)gid + slot, v[0]);
+        const float total_v = warp_reduce16_smem(v, wred, lane);
+        if (lane < 16) {
+          if (GEO ? (lane != 11 && lane != 15) : (lane < 11)) atomicAdd(arena_f + 16 * (size_t)gid + lane, total_v);
         }
       }
       __syncwarp();  // all lanes are done with buf before the step after next overwrites it
     }
     cp_async_wait<0>();
   }
-
-  // ---- dense per-pixel phase: the recorded median-buffer pairs (backward.cu:693-767, 773-804) ----
-  if (GEO && inside && ent_n > 0) {
-    // per-pixel constants of the valid source views: independent loads, all in flight together
-    int sidx[MAX_SRC];
-#pragma unroll
-    for (int mm = 0; mm < MAX_SRC; mm++) sidx[mm] = a.valid_idx[mm * HW + pix_id];
-    const float inv_sumw = __fdividef(1.f, a.sum_w[pix_id]);
-    const float depth_pix = a.depth_pixels[pix_id];
-    int nvalid = MAX_SRC;
-#pragma unroll
-    for (int mm = MAX_SRC - 1; mm >= 0; mm--)
-      if (sidx[mm] == -1) nvalid = mm;   // slots past the terminator are uninitialised and never used
-    float inv_vw[MAX_SRC], dLw[MAX_SRC][3], wpix[MAX_SRC][3];
-#pragma unroll
-    for (int mm = 0; mm < MAX_SRC; mm++) {
-      if (mm < nvalid) {
-        inv_vw[mm] = __fdividef(1.f, a.valid_w[mm * HW + pix_id]);
-#pragma unroll
-        for (int n_i = 0; n_i < 3; n_i++) {
-          dLw[mm][n_i] = a.dL_dwarped[mm * 3 * HW + n_i * HW + pix_id];
-          wpix[mm][n_i] = a.warped_pixels[mm * 3 * HW + n_i * HW + pix_id];
-        }
-      }
-    }
-    const float A_val = (pixf.x - cx) / fx;
-    const float B_val = (pixf.y - cy) / fy;
+  // ---- phase B: this pixel's recorded median-buffer pairs (its own writes above: no fence needed) ----
+  if (GEO && inside) {
 #pragma unroll 1
-    for (int e = 0; e < ent_n; e++) {
-      uint32_t gid = 0;
-      float Te = 0.f, base = 0.f;
-#pragma unroll
-      for (int k = 0; k < MAXE; k++)
-        if (e == k) { gid = ent_id[k]; Te = ent_T[k]; base = ent_base[k]; }
-      const float4* r = a.rec + 4 * (size_t)gid;
-      const float4 g0 = __ldg(r + 0), g1 = __ldg(r + 1), g2 = __ldg(r + 2), g3 = __ldg(r + 3);
-      const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
-      const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
-      const float G = expf(power);
-      const float alpha = min(0.99f, g1.y * G);
-      const float dchannel_dcolor = alpha * Te;
-      float dL_dalpha = base;
-      float dL_dall_map_temp[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-
-      const float3 normal_gauss = {g3.x, g3.y, g3.z};
-      const float distance_gauss = g2.w;
-      const float tmp_gauss = (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
-      const float tmp_gauss2 = distance_gauss / (tmp_gauss * tmp_gauss);
-      const float intersected_depth =
-          -distance_gauss / (normal_gauss.x * ray.x + normal_gauss.y * ray.y + normal_gauss.z + 1.0e-8);
-      const float3 ip = {(pixf.x - cx) * intersected_depth / fx, (pixf.y - cy) * intersected_depth / fy,
-                         intersected_depth};
-      float dL_dz = dL_ddepth * dchannel_dcolor * inv_sumw;
-      dL_dalpha += dL_ddepth * (intersected_depth - depth_pix) * inv_sumw;
-#pragma unroll
-      for (int mm = 0; mm < MAX_SRC; mm++) {
-        if (mm < nvalid) {
-          const int src_idx = sidx[mm];
-          const float* r2s = &s_ref_to_src[src_idx * 16];
-          const float3 tp = {r2s[0] * ip.x + r2s[1] * ip.y + r2s[2] * ip.z + r2s[3],
-                             r2s[4] * ip.x + r2s[5] * ip.y + r2s[6] * ip.z + r2s[7],
-                             r2s[8] * ip.x + r2s[9] * ip.y + r2s[10] * ip.z + r2s[11]};
-          const float2 pp = {(tp.x * fx / tp.z) + cx, (tp.y * fy / tp.z) + cy};
-          if (pp.x >= 0 && pp.x <= W - 1 && pp.y >= 0 && pp.y <= H - 1) {
-            const float4 texC = tex2DLayered<float4>(a.texColor, pp.x + 0.5f, pp.y + 0.5f, src_idx);
-            const float wc[3] = {texC.x, texC.y, texC.z};
-            float dLc[3];
-#pragma unroll
-            for (int n_i = 0; n_i < 3; n_i++) {
-              dLc[n_i] = dLw[mm][n_i] * dchannel_dcolor * inv_vw[mm];
-              dL_dalpha += dLw[mm][n_i] * (wc[n_i] - wpix[mm][n_i]) * inv_vw[mm];
-            }
-            const float U = r2s[0] * A_val + r2s[1] * B_val + r2s[2];
-            const float V = r2s[4] * A_val + r2s[5] * B_val + r2s[6];
-            const float W_coeff = r2s[8] * A_val + r2s[9] * B_val + r2s[10];
-            const float r0 = r2s[3], r1 = r2s[7], r2 = r2s[11];
-            const float denom = (W_coeff * intersected_depth + r2);
-            const float inv_d2 = __fdividef(1.f, denom * denom);
-            const float dp_x_dd = fx * (U * r2 - W_coeff * r0) * inv_d2;
-            const float dp_y_dd = fy * (V * r2 - W_coeff * r1) * inv_d2;
-            const float2 dpp = bilinearInterpolateBackward(src_idx, a.texColor, pp, make_float3(dLc[0], dLc[1], dLc[2]));
-            const float from_color = dpp.x * dp_x_dd + dpp.y * dp_y_dd;
-            dL_dz += from_color;
-            // accumulated inside the view loop, exactly like backward.cu:757-763
-            dL_dall_map_temp[4] += (-dL_dz / tmp_gauss);
-            dL_dall_map_temp[0] += dL_dz * tmp_gauss2 * ray.x;
-            dL_dall_map_temp[1] += dL_dz * tmp_gauss2 * ray.y;
-            dL_dall_map_temp[2] += dL_dz * tmp_gauss2;
-          }
-        }
-      }
-      dL_dalpha *= Te;
-      dL_dalpha += (-T_final * __fdividef(1.f, 1.f - alpha)) * bg_dot_dpixel;
-      const float dL_dG = g1.y * dL_dalpha;
-      const float gdx = G * d.x;
-      const float gdy = G * d.y;
-      const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-      const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-      float4 f0, f1;
-      f0.x = dL_dG * dG_ddelx * ddelx_dx;
-      f0.y = dL_dG * dG_ddely * ddely_dy;
-      f0.z = fabs(dL_dG * dG_ddelx * ddelx_dx);
-      f0.w = fabs(dL_dG * dG_ddely * ddely_dy);
-      f1.x = -0.5f * gdx * d.x * dL_dG;
-      f1.y = -0.5f * gdx * d.y * dL_dG;
-      f1.z = -0.5f * gdy * d.y * dL_dG;
-      f1.w = G * dL_dalpha;
-      float4* dst = a.arena + 4 * (size_t)gid;
-      atomicAdd(dst + 0, f0);
-      atomicAdd(dst + 1, f1);
-      if (dL_dall_map_temp[4] != 0.f || dL_dall_map_temp[0] != 0.f || dL_dall_map_temp[1] != 0.f ||
-          dL_dall_map_temp[2] != 0.f) {
-        atomicAdd(arena_f + 16 * (size_t)gid + 11, dL_dall_map_temp[4]);
-        atomicAdd(dst + 3, make_float4(dL_dall_map_temp[0], dL_dall_map_temp[1], dL_dall_map_temp[2], 0.f));
-      }
-    }
+    for (int e = 0; e < ent_n; e++) median_pair_backward<NSRC>(a, s_ref_to_src, pix, pix_id, e);
   }
 }
 
+constexpr int BWD_SMEM_BYTES = 8 * 2 * 4 * 32 * 16 + 8 * RED_WARP_FLOATS * 4 + MAX_SRC * 16 * 4;
+
+inline int max_entries(int buffer_length) { return buffer_length <= 4 ? 5 : 9; }
+
 }  // namespace
+
+size_t render_backward_scratch_bytes(size_t N, int buffer_length, int render_geo) {
+  if (!render_geo) return 0;
+  const size_t E = (size_t)max_entries(buffer_length);
+  return 3 * align_up(E * N * 4, 256);
+}
 
 int launch_render_backward(const IbgsBackwardArgs& f, const GeomState& g, const ImageState& im,
                            const BinningState& b, TexPair tex, float focal_x, float focal_y, dim3 grid,
-                           float4* arena, cudaStream_t s) {
+                           float4* arena, void* ent_scratch, cudaStream_t s) {
   BwdArgs a;
   a.ranges = im.ranges;
   a.point_list = b.point_list;
@@ -512,15 +569,35 @@ int launch_render_backward(const IbgsBackwardArgs& f, const GeomState& g, const 
   a.dL_ddepths = f.dL_dout_median_intersected_depth;
   a.dL_dwarped = f.dL_dout_warped_image;
   a.arena = arena;
-  ProfScope prof(PROF_RENDER_BWD, s);
+  a.ent = nullptr;
+  a.ent_stride = 0;
+  const size_t N = (size_t)a.W * a.H;
+  const int E = max_entries(f.view.buffer_length);
   if (f.view.render_geo) {
-    if (f.view.buffer_length <= 4)
-      render_backward_kernel<true, 5><<<grid, 256, 0, s>>>(a);
-    else
-      render_backward_kernel<true, 9><<<grid, 256, 0, s>>>(a);
-  } else {
-    render_backward_kernel<false, 1><<<grid, 256, 0, s>>>(a);
+    if (!ent_scratch) { ibgs_set_error("render_geo backward needs its entry scratch"); return IBGS_EINVAL; }
+    char* p = (char*)ent_scratch;
+    a.ent = (float*)p;
+    a.ent_stride = align_up((size_t)E * N * 4, 256) / 4;
   }
+  ProfScope prof(PROF_RENDER_BWD, s);
+  // > 48 KB of shared memory needs the opt-in attribute (per device; cheap enough to set per launch)
+#define LAUNCH_PAIRS(...)                                                                                      \
+  do {                                                                                                         \
+    CUDA_TRY(cudaFuncSetAttribute(render_backward_pairs_kernel<__VA_ARGS__>,                                   \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));               \
+    render_backward_pairs_kernel<__VA_ARGS__><<<grid, 256, BWD_SMEM_BYTES, s>>>(a);                            \
+  } while (0)
+  if (f.view.render_geo) {
+    const bool few = f.view.nb_src_images <= 4;  // the callers' default is 4 source views (arguments/__init__.py:127)
+    if (f.view.buffer_length <= 4) {
+      if (few) LAUNCH_PAIRS(true, 5, 4); else LAUNCH_PAIRS(true, 5, MAX_SRC);
+    } else {
+      if (few) LAUNCH_PAIRS(true, 9, 4); else LAUNCH_PAIRS(true, 9, MAX_SRC);
+    }
+  } else {
+    LAUNCH_PAIRS(false, 1, 1);
+  }
+#undef LAUNCH_PAIRS
   KERNEL_CHECK(f.view.debug, s);
   return IBGS_OK;
 }

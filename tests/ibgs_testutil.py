@@ -108,7 +108,7 @@ def decode_ours(state):
         means2D=rec[:, 0:2], conic_opacity=torch.cat([rec[:, 2:5], rec[:, 5:6]], dim=1), cull_tau=rec[:, 6],
         rgb=rec[:, 8:11], plane_d=rec[:, 11], plane_n=rec[:, 12:15],
         depths=view(g, go[1], P, torch.float32), tiles_touched=view(g, go[2], P, torch.int32),
-        point_offsets=view(g, go[3], P, torch.int32), clamped=view(g, go[4], P, torch.uint8))
+        clamped=view(g, go[3], P, torch.uint8))
     io, _ = N.state_layout(N.IBGS_BUF_IMAGE, Npix, T)
     out.update(final_T=view(im, io[0], Npix, torch.float32), n_contrib=view(im, io[1], Npix, torch.int32),
                sum_w=view(im, io[2], Npix, torch.float32), low=view(im, io[3], Npix, torch.int32),
@@ -117,10 +117,15 @@ def decode_ours(state):
                valid_w=view(im, io[6], 5 * Npix, torch.float32).view(5, Npix),
                ranges=view(im, io[7], 2 * T, torch.int32).view(T, 2))
     out["point_list"] = view(b, 0, R, torch.int32)
-    so, _ = N.state_layout(N.IBGS_BUF_SCRATCH, R, P)
-    out["keys_unsorted"] = view(sc, so[0], R, torch.int64)
-    out["keys"] = view(sc, so[1], R, torch.int64)
+    so, _ = N.state_layout(N.IBGS_BUF_SCRATCH, R, T)
+    out["tiles_unsorted"] = view(sc, so[0], R, torch.int32)
+    out["tiles_sorted"] = view(sc, so[1], R, torch.int32)
     out["point_list_unsorted"] = view(sc, so[2], R, torch.int32)
+    # the reference's 64-bit sort keys (tile id << 32 | depth bits, rasterizer_impl.cu:219-223) rebuilt from
+    # this implementation's state: tile id of every instance + depth of the Gaussian it points to
+    dbits = out["depths"].view(torch.int32).long()
+    out["keys"] = (out["tiles_sorted"].long() << 32) | dbits[out["point_list"].long()]
+    out["keys_unsorted"] = (out["tiles_unsorted"].long() << 32) | dbits[out["point_list_unsorted"].long()]
     return out
 
 

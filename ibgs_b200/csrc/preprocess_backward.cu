@@ -9,9 +9,18 @@
 // backward renderer and writes EVERY output row (zeros for culled Gaussians), so the caller needs no
 // zero-filled gradient tensors (the reference binding memsets eleven of them, rasterize_points.cu:209-219)
 // and dL_dcov3D never round-trips through memory unless cov3D was precomputed.
+//
+// Memory access: one thread per Gaussian, but the two wide per-Gaussian rows -- the SH coefficients (read) and
+// their gradient (written), 12*M bytes each, i.e. 2 x 108 B of the ~480 B a Gaussian moves at M = 9 -- go
+// through a per-warp shared-memory tile: the warp copies its 32 rows with fully coalesced 128-byte accesses and
+// every lane then works on its own row at an odd word stride (bank-conflict free).  Culled Gaussians' SH rows
+// are not read at all; their gradient rows are written as zeros by the same coalesced copy.
 #include "common.cuh"
 
 namespace {
+
+#define PB_THREADS 128
+#define PB_WARPS (PB_THREADS / 32)
 
 struct PBArgs {
   int P, D, M;
@@ -27,6 +36,8 @@ struct PBArgs {
   const float* proj;
   float h_x, h_y, tan_fovx, tan_fovy;
   float half_w, half_h;
+  uint32_t magic;  // floor(2^32 / (3M)) + 1: word index -> row by multiply-high
+  int vec_ok;      // shs and dL_dsh are 16-byte aligned
   const float* campos;
   const float4* arena;
   int has_all_map;
@@ -64,23 +75,45 @@ __forceinline__ __device__ void write_zero_row(const PBArgs& a, int idx) {
     p = a.dL_dcov3D + 6 * (size_t)idx;
     for (int i = 0; i < 6; i++) p[i] = 0.f;
   }
-  if (a.dL_dsh) {
-    p = a.dL_dsh + (size_t)idx * a.M * 3;
-    for (int i = 0; i < a.M * 3; i++) p[i] = 0.f;
-  }
   p = a.dL_dscales + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f;
   reinterpret_cast<float4*>(a.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   p = a.dL_dall_map + 5 * (size_t)idx;
   for (int i = 0; i < 5; i++) p[i] = 0.f;
 }
 
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.P) return;
-  if (!(a.radii[idx] > 0)) {
-    write_zero_row(a, idx);
-    return;
+// warp-cooperative copy between the warp's [32][L] block of global rows (contiguous words, 16-byte aligned because
+// it starts at a multiple of 32 rows) and its shared-memory tile (row stride Ls = L|1 words).  The block is moved
+// as float4 (fully coalesced 512-byte requests); word i of the block belongs to row i / L, computed with a
+// multiply-high (`magic` = floor(2^32 / L) + 1, exact for i < 2^16).
+template <bool STORE>
+__device__ __forceinline__ void tile_copy(float* tile, float* gblock, int nwords, int L, int Ls, uint32_t magic,
+                                          bool vec_ok, int lane) {
+  const int pad = Ls - L;
+  // nwords is a multiple of 4 for a full block of 32 rows; the tail (and everything, if the caller's tensors are
+  // not 16-byte aligned) goes through the scalar loop below
+  const int nvec = vec_ok ? (nwords >> 2) : 0;
+  float4* g4 = reinterpret_cast<float4*>(gblock);
+  for (int i4 = lane; i4 < nvec; i4 += 32) {
+    const int i = i4 << 2;
+    int t[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) t[j] = i + j + pad * (int)__umulhi((uint32_t)(i + j), magic);
+    if (STORE) {
+      g4[i4] = make_float4(tile[t[0]], tile[t[1]], tile[t[2]], tile[t[3]]);
+    } else {
+      const float4 v = g4[i4];
+      tile[t[0]] = v.x; tile[t[1]] = v.y; tile[t[2]] = v.z; tile[t[3]] = v.w;
+    }
   }
+  for (int i = (nvec << 2) + lane; i < nwords; i += 32) {  // partial last block (P not a multiple of 32)
+    const int t = i + pad * (int)__umulhi((uint32_t)i, magic);
+    if (STORE) gblock[i] = tile[t]; else tile[t] = gblock[i];
+  }
+}
+
+// everything for one visible Gaussian; `shrow` is its SH row in the warp's shared-memory tile: coefficients on
+// entry, their gradient on exit (every word of the row is overwritten)
+__device__ __forceinline__ void preprocess_backward_one(const PBArgs& a, int idx, float* shrow) {
   // slots 0-6 arrive unscaled from the tile renderer (render_backward.cu): apply 0.5*W, 0.5*H
   // (backward.cu:606-607) and the -0.5 of the conic terms (:799-801) once per Gaussian
   float4 a0 = a.arena[4 * (size_t)idx + 0];
@@ -226,8 +259,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a
     const float3 dir_orig = {m.x - campos.x, m.y - campos.y, m.z - campos.z};
     const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
     const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-    const float* sh = a.shs + (size_t)idx * a.M * 3;
-    float* dL_dsh = a.dL_dsh + (size_t)idx * a.M * 3;
+    // The gradient row overwrites the coefficient row in place (same shared-memory words), so each degree band
+    // first pulls its coefficients into registers, then writes its gradients.
+    float* dL_dsh = shrow;
     const uint8_t cl = a.clamped[idx];
     float dRGB[3] = {a2.x, a2.y, a2.z};
 #pragma unroll
@@ -238,6 +272,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a
 #pragma unroll
     for (int c = 0; c < 3; c++) dL_dsh[c] = SH_C0 * dRGB[c];
     if (deg > 0) {
+      float sh[12];
+#pragma unroll
+      for (int k = 3; k < 12; k++) sh[k] = shrow[k];
       const float d1 = -SH_C1 * y, d2 = SH_C1 * z, d3 = -SH_C1 * x;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -250,6 +287,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a
       }
       written = 4;
       if (deg > 1) {
+        float sh2[27];
+#pragma unroll
+        for (int k = 12; k < 27; k++) sh2[k] = shrow[k];
         const float xx = x * x, yy = y * y, zz = z * z;
         const float xy = x * y, yz = y * z, xz = x * z;
         const float d4 = SH_C2[0] * xy, d5 = SH_C2[1] * yz, d6 = SH_C2[2] * (2.f * zz - xx - yy),
@@ -261,14 +301,17 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a
           dL_dsh[18 + c] = d6 * dRGB[c];
           dL_dsh[21 + c] = d7 * dRGB[c];
           dL_dsh[24 + c] = d8 * dRGB[c];
-          dRGBdx[c] += SH_C2[0] * y * sh[12 + c] + SH_C2[2] * 2.f * -x * sh[18 + c] + SH_C2[3] * z * sh[21 + c] +
-                       SH_C2[4] * 2.f * x * sh[24 + c];
-          dRGBdy[c] += SH_C2[0] * x * sh[12 + c] + SH_C2[1] * z * sh[15 + c] + SH_C2[2] * 2.f * -y * sh[18 + c] +
-                       SH_C2[4] * 2.f * -y * sh[24 + c];
-          dRGBdz[c] += SH_C2[1] * y * sh[15 + c] + SH_C2[2] * 2.f * 2.f * z * sh[18 + c] + SH_C2[3] * x * sh[21 + c];
+          dRGBdx[c] += SH_C2[0] * y * sh2[12 + c] + SH_C2[2] * 2.f * -x * sh2[18 + c] + SH_C2[3] * z * sh2[21 + c] +
+                       SH_C2[4] * 2.f * x * sh2[24 + c];
+          dRGBdy[c] += SH_C2[0] * x * sh2[12 + c] + SH_C2[1] * z * sh2[15 + c] + SH_C2[2] * 2.f * -y * sh2[18 + c] +
+                       SH_C2[4] * 2.f * -y * sh2[24 + c];
+          dRGBdz[c] += SH_C2[1] * y * sh2[15 + c] + SH_C2[2] * 2.f * 2.f * z * sh2[18 + c] + SH_C2[3] * x * sh2[21 + c];
         }
         written = 9;
         if (deg > 2) {
+          float sh3[48];
+#pragma unroll
+          for (int k = 27; k < 48; k++) sh3[k] = shrow[k];
           const float d9 = SH_C3[0] * y * (3.f * xx - yy), d10 = SH_C3[1] * xy * z,
                       d11 = SH_C3[2] * y * (4.f * zz - xx - yy),
                       d12 = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy),
@@ -283,17 +326,17 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a
             dL_dsh[39 + c] = d13 * dRGB[c];
             dL_dsh[42 + c] = d14 * dRGB[c];
             dL_dsh[45 + c] = d15 * dRGB[c];
-            dRGBdx[c] += (SH_C3[0] * sh[27 + c] * 3.f * 2.f * xy + SH_C3[1] * sh[30 + c] * yz +
-                          SH_C3[2] * sh[33 + c] * -2.f * xy + SH_C3[3] * sh[36 + c] * -3.f * 2.f * xz +
-                          SH_C3[4] * sh[39 + c] * (-3.f * xx + 4.f * zz - yy) + SH_C3[5] * sh[42 + c] * 2.f * xz +
-                          SH_C3[6] * sh[45 + c] * 3.f * (xx - yy));
-            dRGBdy[c] += (SH_C3[0] * sh[27 + c] * 3.f * (xx - yy) + SH_C3[1] * sh[30 + c] * xz +
-                          SH_C3[2] * sh[33 + c] * (-3.f * yy + 4.f * zz - xx) +
-                          SH_C3[3] * sh[36 + c] * -3.f * 2.f * yz + SH_C3[4] * sh[39 + c] * -2.f * xy +
-                          SH_C3[5] * sh[42 + c] * -2.f * yz + SH_C3[6] * sh[45 + c] * -3.f * 2.f * xy);
-            dRGBdz[c] += (SH_C3[1] * sh[30 + c] * xy + SH_C3[2] * sh[33 + c] * 4.f * 2.f * yz +
-                          SH_C3[3] * sh[36 + c] * 3.f * (2.f * zz - xx - yy) +
-                          SH_C3[4] * sh[39 + c] * 4.f * 2.f * xz + SH_C3[5] * sh[42 + c] * (xx - yy));
+            dRGBdx[c] += (SH_C3[0] * sh3[27 + c] * 3.f * 2.f * xy + SH_C3[1] * sh3[30 + c] * yz +
+                          SH_C3[2] * sh3[33 + c] * -2.f * xy + SH_C3[3] * sh3[36 + c] * -3.f * 2.f * xz +
+                          SH_C3[4] * sh3[39 + c] * (-3.f * xx + 4.f * zz - yy) + SH_C3[5] * sh3[42 + c] * 2.f * xz +
+                          SH_C3[6] * sh3[45 + c] * 3.f * (xx - yy));
+            dRGBdy[c] += (SH_C3[0] * sh3[27 + c] * 3.f * (xx - yy) + SH_C3[1] * sh3[30 + c] * xz +
+                          SH_C3[2] * sh3[33 + c] * (-3.f * yy + 4.f * zz - xx) +
+                          SH_C3[3] * sh3[36 + c] * -3.f * 2.f * yz + SH_C3[4] * sh3[39 + c] * -2.f * xy +
+                          SH_C3[5] * sh3[42 + c] * -2.f * yz + SH_C3[6] * sh3[45 + c] * -3.f * 2.f * xy);
+            dRGBdz[c] += (SH_C3[1] * sh3[30 + c] * xy + SH_C3[2] * sh3[33 + c] * 4.f * 2.f * yz +
+                          SH_C3[3] * sh3[36 + c] * 3.f * (2.f * zz - xx - yy) +
+                          SH_C3[4] * sh3[39 + c] * 4.f * 2.f * xz + SH_C3[5] * sh3[42 + c] * (xx - yy));
           }
           written = 16;
         }
@@ -360,6 +403,39 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(const PBArgs a
   }
 }
 
+__global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const PBArgs a) {
+  extern __shared__ float s_tiles[];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int L = a.M * 3;        // words per SH row
+  const int Ls = L | 1;         // odd stride: conflict-free row access
+  float* tile = s_tiles + (threadIdx.x >> 5) * (32 * Ls);
+  const size_t row0 = (size_t)idx - lane;
+  if (row0 >= (size_t)a.P) return;  // whole warp out of range
+  const int rows = min(32, a.P - (int)row0);
+  const bool in_range = idx < a.P;
+  const bool visible = in_range && (a.radii[idx] > 0);
+  const bool any_visible = __any_sync(0xffffffffu, visible);
+  const bool has_sh = a.shs != nullptr;
+  if (has_sh && any_visible) {
+    tile_copy<false>(tile, const_cast<float*>(a.shs) + row0 * L, rows * L, L, Ls, a.magic, a.vec_ok != 0, lane);
+    __syncwarp();
+  }
+  if (visible) {
+    preprocess_backward_one(a, idx, tile + lane * Ls);
+  } else if (in_range) {
+    write_zero_row(a, idx);
+    if (has_sh) {
+      float* row = tile + lane * Ls;
+      for (int k = 0; k < L; k++) row[k] = 0.f;
+    }
+  }
+  if (has_sh) {
+    __syncwarp();
+    tile_copy<true>(tile, a.dL_dsh + row0 * L, rows * L, L, Ls, a.magic, a.vec_ok != 0, lane);
+  }
+}
+
 }  // namespace
 
 int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, const float4* arena,
@@ -378,6 +454,8 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.cov3D_precomp = f.cov3D_precomp;
   a.view = f.view.viewmatrix;
   a.proj = f.view.projmatrix;
+  a.magic = (a.M > 0) ? (uint32_t)(0x100000000ull / (uint64_t)(a.M * 3)) + 1u : 0u;
+  a.vec_ok = ((((uintptr_t)f.shs) | ((uintptr_t)f.dL_dsh)) & 15u) == 0;
   a.half_w = (float)(0.5 * f.view.image_width);
   a.half_h = (float)(0.5 * f.view.image_height);
   a.h_x = focal_x;
@@ -398,7 +476,8 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.dL_drotations = f.dL_drotations;
   a.dL_dall_map = f.dL_dall_map;
   ProfScope prof(PROF_PREPROCESS_BWD, s);
-  preprocess_backward_kernel<<<(f.P + 255) / 256, 256, 0, s>>>(a);
+  const size_t smem = (size_t)PB_WARPS * 32 * ((a.M * 3) | 1) * sizeof(float);
+  preprocess_backward_kernel<<<(f.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, smem, s>>>(a);
   KERNEL_CHECK(f.view.debug, s);
   return IBGS_OK;
 }

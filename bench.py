@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg3_1080p")
-    ap.add_argument("--views-per-step", type=int, default=2)
+    # the data-parallel step is a batch of 8 views per GPU (gradient accumulation) followed
+    # by one all-reduce of the per-Gaussian gradient arena
+    ap.add_argument("--views-per-step", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -275,7 +277,7 @@ class HostStager:
         self.counter += 1
 
 
-PREWARM_STEPS = 6   # untimed set-up passes: let torch's caching allocator reach its steady state (the per-view
+PREWARM_STEPS = 2   # untimed set-up passes: let torch's caching allocator reach its steady state (the per-view
                     # state buffers are tens of MB to GB; a cold cache means cudaMalloc + implicit syncs)
 
 

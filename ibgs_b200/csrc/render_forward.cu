@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
     a.out_camera_ray[2 * HW + pix_id] = ray_dir.z;
 
     int valid_src_count = 0;
+    bool first_valid = false;
     float min_depth_error = 1.0f;
 #pragma unroll
     for (int s = 0; s < MAX_SRC; s++) {
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
           sd.z /= sl;
           const float ray_dir_diff = sd.x * ray_dir.x + sd.y * ray_dir.y + sd.z * ray_dir.z;
           a.out_cam_feat[valid_src_count * 4 * HW + 3 * HW + pix_id] = ray_dir_diff;
-          if (s == 0) a.out_mask[pix_id] = 1;
+          if (s == 0) first_valid = true;
           a.valid_idx[valid_src_count * HW + pix_id] = s;
           a.valid_w[valid_src_count * HW + pix_id] = total_w_src[s];
           valid_src_count++;
@@ -382,6 +383,16 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
       }
     }
     if (valid_src_count <= MAX_SRC - 1) a.valid_idx[valid_src_count * HW + pix_id] = -1;
+    // Unused slots and the first-source mask are written as zeros HERE: in render_geo mode this kernel writes every
+    // word of every output, so the caller needs no zero-filled tensors (the reference binding memsets all nine
+    // outputs with torch::full, rasterize_points.cu:80-90, and relies on that for these slots).
+    a.out_mask[pix_id] = first_valid ? 1 : 0;
+    for (int k = valid_src_count; k < MAX_SRC; k++) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) a.out_cam_feat[(k * 4 + c) * HW + pix_id] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 3; c++) a.out_warped[(k * 3 + c) * HW + pix_id] = 0.0f;
+    }
     a.out_min_depth_diff[pix_id] = min_depth_error;
     a.out_depth[pix_id] = median_intersected_depth;
 #pragma unroll

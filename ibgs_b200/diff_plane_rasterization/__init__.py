@@ -132,18 +132,22 @@ class _RasterizeGaussians(torch.autograd.Function):
         cov_c = _f32c(cov3Ds_precomp, device)
         allmap_c = _f32c(all_maps, device)
 
+        # The reference binding zero-fills all nine outputs (torch::full, rasterize_points.cu:80-90) and its kernels
+        # leave unused slots untouched.  In render_geo mode our tile renderer writes every word of every output
+        # (zeros included) and preprocess writes every radius, so torch.empty is enough; in the other modes the
+        # untouched outputs must read as zeros.  (Separate tensors on purpose: callers keep single outputs alive.)
+        make = torch.empty if (rs.render_geo and P > 0) else torch.zeros
         fopt = dict(dtype=torch.float32, device=device)
         iopt = dict(dtype=torch.int32, device=device)
-        # zero-initialised like the binding's torch::full (rasterize_points.cu:80-90): unused slots stay 0
-        color = torch.zeros((3, H, W), **fopt)
-        radii = torch.zeros((P,), **iopt)
-        out_normal_map = torch.zeros((3, H, W), **fopt)
-        out_median_intersected_depth = torch.zeros((1, H, W), **fopt)
-        out_cam_feat = torch.zeros((4 * _M, H, W), **fopt)
-        out_warped_image = torch.zeros((3 * _M, H, W), **fopt)
-        out_min_depth_diff = torch.zeros((1, H, W), **fopt)
-        out_camera_ray = torch.zeros((3, H, W), **fopt)
-        out_use_first_src_frame = torch.zeros((1, H, W), **iopt)
+        color = make((3, H, W), **fopt)
+        radii = make((P,), **iopt)
+        out_normal_map = make((3, H, W), **fopt)
+        out_median_intersected_depth = make((1, H, W), **fopt)
+        out_cam_feat = make((4 * _M, H, W), **fopt)
+        out_warped_image = make((3 * _M, H, W), **fopt)
+        out_min_depth_diff = make((1, H, W), **fopt)
+        out_camera_ray = make((3, H, W), **fopt)
+        out_use_first_src_frame = make((1, H, W), **iopt)
 
         alloc = _Allocator(device)
         keep = []

@@ -95,29 +95,46 @@ __forceinline__ __device__ float2 bilinearInterpolateBackward(int src_idx, cudaT
 // Every lane holds 16 partial gradient terms of ONE Gaussian (its own pixel's share); the warp needs the 16
 // column sums.  A shuffle butterfly costs 31 SHFL + 62 SEL + 31 FADD per Gaussian; transposing through shared
 // memory costs 4 STS.128 + 16 LDS + 16 FADD + 1 SHFL:
-//   * lane l stores its 16 values as row l of a [32][16] float tile (4 x STS.128).  The float4 column index is
-//     XOR-swizzled with (l>>1)&3 and rows 16..31 are shifted by one 16-float pad, which makes both the
-//     quarter-warp STS.128 phases and the scalar column reads below bank-conflict free;
-//   * lane (s = l&15, h = l>>4) then sums column s over rows 16h..16h+15 (16 scalar LDS: the two half-warps
-//     read rows of opposite parity -> disjoint bank halves; within a half the swizzle permutes 16 banks);
+//   * lane l stores its 16 values as row l of a [32][16] float tile (4 x STS.128).  Rows are 20 words apart
+//     (l*20 mod 32 walks all eight 4-bank groups over a quarter-warp, so the 128-bit stores are conflict free) and
+//     rows 16..31 sit 16 words further (the two half-warps then read disjoint bank halves);
+//   * lane (s = l&15, h = l>>4) sums column s over rows 16h..16h+15 with four independent partial sums (16 scalar
+//     LDS at immediate offsets from one base register);
 //   * one xor-16 shuffle adds the two halves.  On return lanes 0..15 hold the total of slot `lane`.
-#define RED_ROW_FLOATS 16
-#define RED_WARP_FLOATS (33 * RED_ROW_FLOATS)
-__forceinline__ __device__ float warp_reduce16_smem(const float (&v)[16], float* red, int lane) {
+// Both addresses are 32-bit shared-window offsets computed once per thread and used through inline PTX, so the
+// per-Gaussian cost carries no address arithmetic.
+#define RED_ROW_WORDS 20
+#define RED_WARP_FLOATS (32 * RED_ROW_WORDS + 16)
+__device__ __forceinline__ uint32_t red_store_addr(const float* red, int lane) {
+  return (uint32_t)__cvta_generic_to_shared(red + lane * RED_ROW_WORDS + (lane >> 4) * 16);
+}
+__device__ __forceinline__ uint32_t red_load_addr(const float* red, int lane) {
+  return (uint32_t)__cvta_generic_to_shared(red + (lane >> 4) * (16 * RED_ROW_WORDS + 16) + (lane & 15));
+}
+template <int OFF>
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0+%1], {%2, %3, %4, %5};" ::"r"(addr), "n"(OFF), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float x;
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(x) : "r"(addr), "n"(OFF) : "memory");
+  return x;
+}
+__forceinline__ __device__ float warp_reduce16_smem(const float (&v)[16], uint32_t st_addr, uint32_t ld_addr) {
   constexpr unsigned FULL = 0xffffffffu;
-  {
-    float4* row = reinterpret_cast<float4*>(red) + (lane * 4 + (lane >> 4) * 4);
-    const int cl = (lane >> 1) & 3;
-#pragma unroll
-    for (int q = 0; q < 4; q++) row[q ^ cl] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-  }
+  constexpr int RB = RED_ROW_WORDS * 4;  // row pitch in bytes
+  sts128<0>(st_addr, v[0], v[1], v[2], v[3]);
+  sts128<16>(st_addr, v[4], v[5], v[6], v[7]);
+  sts128<32>(st_addr, v[8], v[9], v[10], v[11]);
+  sts128<48>(st_addr, v[12], v[13], v[14], v[15]);
   __syncwarp();
-  const int s = lane & 15, h = lane >> 4;
-  const float* col = red + h * (16 * RED_ROW_FLOATS + RED_ROW_FLOATS) + (s & 3);
-  const int sq = s >> 2;
-  float sum = 0.0f;
-#pragma unroll
-  for (int k = 0; k < 16; k++) sum += col[k * RED_ROW_FLOATS + ((sq ^ ((k >> 1) & 3)) << 2)];
+  const float s0 = (lds32<0 * RB>(ld_addr) + lds32<1 * RB>(ld_addr)) + (lds32<2 * RB>(ld_addr) + lds32<3 * RB>(ld_addr));
+  const float s1 = (lds32<4 * RB>(ld_addr) + lds32<5 * RB>(ld_addr)) + (lds32<6 * RB>(ld_addr) + lds32<7 * RB>(ld_addr));
+  const float s2 = (lds32<8 * RB>(ld_addr) + lds32<9 * RB>(ld_addr)) + (lds32<10 * RB>(ld_addr) + lds32<11 * RB>(ld_addr));
+  const float s3 = (lds32<12 * RB>(ld_addr) + lds32<13 * RB>(ld_addr)) + (lds32<14 * RB>(ld_addr) + lds32<15 * RB>(ld_addr));
+  float sum = (s0 + s1) + (s2 + s3);
   sum += __shfl_xor_sync(FULL, sum, 16);
   __syncwarp();  // all reads done before the next Gaussian's rows are stored
   return sum;
@@ -362,7 +379,8 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
 
   float* arena_f = reinterpret_cast<float*>(a.arena);
   float4(*wrec)[4][32] = s_rec[warp];
-  float* wred = s_red_all + warp * RED_WARP_FLOATS;
+  const uint32_t red_st = red_store_addr(s_red_all + warp * RED_WARP_FLOATS, lane);
+  const uint32_t red_ld = red_load_addr(s_red_all + warp * RED_WARP_FLOATS, lane);
 
   // list position p (0 = back of the list) holds contributor index total-1-p; positions with
   // contributor >= warp_max_contrib cannot contribute to any pixel of this warp: start after them
@@ -512,7 +530,7 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
           }
         }
 
-        const float total_v = warp_reduce16_smem(v, wred, lane);
+        const float total_v = warp_reduce16_smem(v, red_st, red_ld);
         if (lane < 16) {
           if (GEO ? (lane != 11 && lane != 15) : (lane < 11)) atomicAdd(arena_f + 16 * (size_t)gid + lane, total_v);
         }

@@ -416,14 +416,15 @@ def main():
         per_launch_ms = bw_ms / bw_n
         # algorithmic bytes of the backward tile renderer: point list + one 64 B record
         # read and one 64 B accumulator write per visible Gaussian + 212 B per pixel of cotangents / saved state
-        alg = 4 * R + 128 * P_vis + 212 * Npix
+        # + the per-pixel median-pair lists (12 B written and read back per entry, <= buffer_length entries)
+        alg = 4 * R + 128 * P_vis + 212 * Npix + 24 * 4 * Npix
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json"))).get("bytes_per_launch")
         except Exception:
             pass
         ach = alg / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "render_backward_kernel<geo>", "achieved": ach, "peak": peak_gbs,
+        roofline = {"bound": "hbm", "kernel": "render_backward_pairs_kernel<geo>", "achieved": ach, "peak": peak_gbs,
                     "unit": "GB/s", "frac": ach / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg, "ms_per_launch": per_launch_ms,
                     "note": "the pair loop is issue/latency bound, not HBM bound (DESIGN.md): see pairs_per_s"}

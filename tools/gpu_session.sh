@@ -18,7 +18,7 @@ IBGS_BENCH_NOCLOCK=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-co
   > $OUT/${TAG}_launches_bench.log 2>&1
 # full capture of the two tile renderers + sort + preprocess backward, one launch each, warm
 timeout 600 ncu --set full --clock-control none --import-source on \
-  -k regex:'render_backward_kernel|render_forward_kernel|preprocess_backward_kernel|preprocess_kernel' -s 12 -c 4 \
+  -k regex:'render_backward_pairs_kernel|render_forward_kernel|preprocess_backward_kernel|preprocess_kernel|emit_instances_kernel' -s 13 -c 5 \
   -f -o $OUT/${TAG}_prof python tools/profile_one.py cfg3_1080p 2 > $OUT/${TAG}_ncu_full.log 2>&1
 tail -3 $OUT/${TAG}_pytest_gpu.log
 cat $OUT/${TAG}_bench_b200.json | cut -c1-600

@@ -118,8 +118,12 @@ def decode_ours(state):
                ranges=view(im, io[7], 2 * T, torch.int32).view(T, 2))
     out["point_list"] = view(b, 0, R, torch.int32)
     so, _ = N.state_layout(N.IBGS_BUF_SCRATCH, R, T)
-    out["tiles_unsorted"] = view(sc, so[0], R, torch.int32)
-    out["tiles_sorted"] = view(sc, so[1], R, torch.int32)
+    if N.lib.ibgs_sort_bits(T) - 32 <= 16:   # tile ids are stored as uint16 up to 65536 tiles (binning.cu)
+        out["tiles_unsorted"] = view(sc, so[0], R, torch.int16).int() & 0xFFFF
+        out["tiles_sorted"] = view(sc, so[1], R, torch.int16).int() & 0xFFFF
+    else:
+        out["tiles_unsorted"] = view(sc, so[0], R, torch.int32)
+        out["tiles_sorted"] = view(sc, so[1], R, torch.int32)
     out["point_list_unsorted"] = view(sc, so[2], R, torch.int32)
     # the reference's 64-bit sort keys (tile id << 32 | depth bits, rasterizer_impl.cu:219-223) rebuilt from
     # this implementation's state: tile id of every instance + depth of the Gaussian it points to

@@ -94,3 +94,20 @@ def test_synthetic_scene_is_deterministic_and_consistent():
         assert torch.allclose(a["ref_to_src_list"][i], w2s @ torch.linalg.inv(w2c), atol=1e-5)
         assert torch.allclose(torch.linalg.inv(w2s)[:3, 3], a["src_cam_pos"][i], atol=1e-5)
     assert c_ref_world.shape == (3,)
+
+
+def test_shim_directory_provides_reference_import_names():
+    """with shims/ on PYTHONPATH the reference's import lines work unchanged."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "shims"), root]))
+    code = ("from diff_plane_rasterization import GaussianRasterizationSettings, GaussianRasterizer\n"
+            "from simple_knn._C import distCUDA2\n"
+            "import ibgs_b200.diff_plane_rasterization as d\n"
+            "assert GaussianRasterizer is d.GaussianRasterizer\n"
+            "assert GaussianRasterizationSettings._fields[:4] == ('image_height', 'image_width', 'tanfovx', 'tanfovy')\n"
+            "print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr

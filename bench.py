@@ -323,6 +323,39 @@ def cpu_baseline(args):
                       f"{dt:.2f}s, scaled x{scale:.0f} (linear in P); float64 C oracle with OpenMP"}
 
 
+def prologue_timing(P, device, K=9, iters=10):
+    """SURVEY.md section 8f rank 1 (next row, reported beside the headline, not part of it): forward+backward of the
+    per-view parameter prologue at the workload's P -- the reference's torch expressions vs ibgs_b200.fused."""
+    import prologue_ref as PR
+    from ibgs_b200 import fused
+    names = ("xyz", "opacity_raw", "scaling_raw", "rotation_raw", "fdc", "frest", "normal_raw", "offset")
+    p = PR.random_params(P, K=K, seed=0, device=device)
+    g = torch.Generator().manual_seed(1)
+    cots = [torch.randn(s, generator=g).to(device) for s in ((P, 1), (P, 3), (P, 4), (P, K, 3), (P, 5))]
+    out = {}
+    for name, fn in (("torch", PR.torch_prologue), ("fused", fused.gaussian_prologue)):
+        leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+
+        def step():
+            for v in leaves.values():
+                v.grad = None
+            torch.autograd.backward(list(fn(*[leaves[k] for k in names], p["V"], p["cam"])), cots)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(device)
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); step(); e1.record(); torch.cuda.synchronize(device)
+            ts.append(e0.elapsed_time(e1))
+        out[name + "_ms_per_view"] = sorted(ts)[len(ts) // 2]
+        del leaves
+    words_in, words_out = 15 + 3 * K, 13 + 3 * K
+    alg = 4 * P * (3 * words_in + 2 * words_out)
+    out["fused_GBps"] = alg / (out["fused_ms_per_view"] * 1e-3) / 1e9
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -455,6 +488,13 @@ def main():
                                           "(oracle/_ref) on the same GPU, full workload"}
     elif args.gpus == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
+    if args.impl == "b200" and args.gpus == 1:
+        try:
+            del runner
+            torch.cuda.empty_cache()
+            line["parameter_prologue"] = prologue_timing(wl.P, device)
+        except Exception as ex:  # extra information only: never lose the headline line over it
+            line["parameter_prologue"] = {"error": repr(ex)}
     print(json.dumps(line))
     if eff_world > 1:
         dist.destroy_process_group()

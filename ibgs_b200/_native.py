@@ -61,11 +61,22 @@ class IbgsBackwardArgs(C.Structure):
     ]
 
 
+class IbgsPrologueArgs(C.Structure):
+    _fields_ = [("P", C.c_int32), ("sh_rest", C.c_int32)] + [(n, _fp) for n in (
+        "xyz", "opacity_raw", "scaling_raw", "rotation_raw", "features_dc", "features_rest", "normal_raw", "offset",
+        "world_view_transform", "camera_center",
+        "opacity", "scales", "rotations", "shs", "all_map",
+        "g_opacity", "g_scales", "g_rotations", "g_shs", "g_all_map",
+        "d_xyz", "d_opacity_raw", "d_scaling_raw", "d_rotation_raw", "d_features_dc", "d_features_rest",
+        "d_normal_raw", "d_offset")]
+
+
 EXPORTS = [
     "ibgs_forward", "ibgs_backward", "ibgs_mark_visible", "ibgs_dist2_scratch_bytes", "ibgs_dist2",
     "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
     "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
-    "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages",
+    "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
+    "ibgs_prologue_backward",
 ]
 
 
@@ -107,6 +118,9 @@ def _load():
     lib.ibgs_profile_name.restype = C.c_char_p
     lib.ibgs_profile_name.argtypes = [C.c_int]
     lib.ibgs_profile_stages.restype = C.c_int
+    for fn in (lib.ibgs_prologue_forward, lib.ibgs_prologue_backward):
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(IbgsPrologueArgs), C.c_void_p]
     return lib
 
 

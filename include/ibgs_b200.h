@@ -158,6 +158,40 @@ size_t ibgs_dist2_scratch_bytes(int32_t P);
 int ibgs_dist2(int32_t P, const float* points, float* mean_dists, void* scratch, size_t scratch_bytes,
                void* stream);
 
+/* Fused per-view parameter prologue (optional fast path, the reference has no such
+ * entry point).  Replaces the ~30 PyTorch kernels gaussian_renderer.render() runs over all Gaussians before every
+ * rasterizer call: the activations of the GaussianModel getters (scene/gaussian_model.py:127-147), the learnt plane
+ * normal (get_normal, :166-173) and the all_map construction (gaussian_renderer/__init__.py:304-315) -- and their
+ * autograd backward.  normal_raw/offset may both be NULL (no all_map, e.g. colour-only renders).  In the backward
+ * call every g_* may be NULL (= zero cotangent) and d_xyz holds only the all_map path's share of dL/dxyz. */
+typedef struct IbgsPrologueArgs {
+  int32_t P;
+  int32_t sh_rest;               /* coefficients per channel in features_rest (K-1) */
+  const float* xyz;              /* [P,3]  _xyz */
+  const float* opacity_raw;      /* [P,1]  _opacity (pre-sigmoid) */
+  const float* scaling_raw;      /* [P,3]  _scaling (log) */
+  const float* rotation_raw;     /* [P,4]  _rotation (un-normalised) */
+  const float* features_dc;      /* [P,1,3] */
+  const float* features_rest;    /* [P,K-1,3] */
+  const float* normal_raw;       /* [P,3]  _normal or NULL */
+  const float* offset;           /* [P,1]  _offset or NULL */
+  const float* world_view_transform; /* [16] */
+  const float* camera_center;    /* [3] */
+  /* forward outputs */
+  float* opacity;                /* [P,1] */
+  float* scales;                 /* [P,3] */
+  float* rotations;              /* [P,4] */
+  float* shs;                    /* [P,K,3] */
+  float* all_map;                /* [P,5] */
+  /* backward inputs (cotangents of the forward outputs) */
+  const float* g_opacity; const float* g_scales; const float* g_rotations; const float* g_shs; const float* g_all_map;
+  /* backward outputs */
+  float* d_xyz; float* d_opacity_raw; float* d_scaling_raw; float* d_rotation_raw;
+  float* d_features_dc; float* d_features_rest; float* d_normal_raw; float* d_offset;
+} IbgsPrologueArgs;
+int ibgs_prologue_forward(const IbgsPrologueArgs* args, void* stream);
+int ibgs_prologue_backward(const IbgsPrologueArgs* args, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds; used by bench.py's e2e arm):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages
  * through its own device arena (cudaMallocAsync) and copies results back before returning. */

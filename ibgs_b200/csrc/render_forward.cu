@@ -250,7 +250,9 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
         T = test_T;
         last_contributor = contributor;
       }
-      if (__all_sync(FULL, done)) break;   // warp-level early termination (also orders the buffer re-use)
+      if (__all_sync(FULL, done)) break;   // warp-level early termination
+      __syncwarp();  // every lane is done reading buf before the step after next overwrites it (a vote is not a
+                     // memory-ordering barrier; compute-sanitizer racecheck flags the re-use without this)
     }
     cp_async_wait<0>();
   }

@@ -34,7 +34,7 @@ class IbgsView(C.Structure):
 class IbgsForwardArgs(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("view", IbgsView),
-        ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp), ("scales", _fp),
+        ("means3D", _fp), ("shs", _fp), ("shs_rest", _fp), ("colors_precomp", _fp), ("opacities", _fp), ("scales", _fp),
         ("rotations", _fp), ("cov3D_precomp", _fp), ("all_map", _fp),
         ("out_color", _fp), ("radii", _fp), ("out_normal_map", _fp), ("out_median_intersected_depth", _fp),
         ("out_cam_feat", _fp), ("out_warped_image", _fp), ("out_min_depth_diff", _fp),
@@ -47,7 +47,7 @@ class IbgsForwardArgs(C.Structure):
 class IbgsBackwardArgs(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("R", C.c_int64), ("view", IbgsView),
-        ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("scales", _fp), ("rotations", _fp),
+        ("means3D", _fp), ("shs", _fp), ("shs_rest", _fp), ("colors_precomp", _fp), ("scales", _fp), ("rotations", _fp),
         ("cov3D_precomp", _fp), ("all_map", _fp), ("radii", _fp),
         ("out_median_intersected_depth", _fp), ("out_warped_image", _fp),
         ("geom_buffer", _fp), ("binning_buffer", _fp), ("image_buffer", _fp),
@@ -55,7 +55,7 @@ class IbgsBackwardArgs(C.Structure):
         ("dL_dout_color", _fp), ("dL_dout_normal_map", _fp), ("dL_dout_median_intersected_depth", _fp),
         ("dL_dout_warped_image", _fp),
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dmeans2D_abs", _fp), ("dL_dcolors", _fp),
-        ("dL_dopacity", _fp), ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dscales", _fp),
+        ("dL_dopacity", _fp), ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dsh_rest", _fp), ("dL_dscales", _fp),
         ("dL_drotations", _fp), ("dL_dall_map", _fp),
         ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p),
     ]

@@ -178,6 +178,10 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
     ibgs_set_error("provide shs or colors_precomp");
     return IBGS_EINVAL;
   }
+  if (a->shs_rest && (!a->shs || v.sh_coeffs < 2)) {
+    ibgs_set_error("shs_rest needs shs (the DC part) and sh_coeffs >= 2");
+    return IBGS_EINVAL;
+  }
   if ((v.render_geo || v.render_depth_only) && !a->all_map) {
     ibgs_set_error("render_geo / render_depth_only need all_map");
     return IBGS_EINVAL;
@@ -268,7 +272,8 @@ extern "C" int ibgs_backward(IbgsBackwardArgs* a, void* stream_v) {
     return IBGS_EINVAL;
   }
   if (!a->dL_dmeans3D || !a->dL_dmeans2D || !a->dL_dmeans2D_abs || !a->dL_dcolors || !a->dL_dopacity ||
-      !a->dL_dscales || !a->dL_drotations || !a->dL_dall_map || (a->shs && !a->dL_dsh)) {
+      !a->dL_dscales || !a->dL_drotations || !a->dL_dall_map || (a->shs && !a->dL_dsh) ||
+      (a->shs && a->shs_rest && !a->dL_dsh_rest)) {
     ibgs_set_error("gradient output pointers must not be NULL");
     return IBGS_EINVAL;
   }

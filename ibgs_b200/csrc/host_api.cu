@@ -68,7 +68,8 @@ extern "C" int64_t ibgs_forward_h(IbgsForwardArgs* h) {
   d.view.src_images = pool.up(hv.src_images, nb * 3 * N);
   d.view.src_rendered_depths = pool.up(hv.src_rendered_depths, nb * N);
   d.means3D = pool.up(h->means3D, P * 3);
-  d.shs = pool.up(h->shs, P * M * 3);
+  d.shs = pool.up(h->shs, h->shs_rest ? P * 3 : P * M * 3);
+  d.shs_rest = pool.up(h->shs_rest, M > 1 ? P * (M - 1) * 3 : 0);
   d.colors_precomp = pool.up(h->colors_precomp, P * 3);
   d.opacities = pool.up(h->opacities, P);
   d.scales = pool.up(h->scales, P * 3);

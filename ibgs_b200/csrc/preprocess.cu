@@ -23,6 +23,7 @@ struct PreArgs {
   const float* rotations;
   const float* opacities;
   const float* shs;
+  const float* shs_rest;
   const float* cov3D_precomp;
   const float* colors_precomp;
   const float* all_map;
@@ -97,17 +98,20 @@ __forceinline__ __device__ float3 computeCov2D(const float3& mean, float focal_x
 
 // reference forward.cu:58-109 (vec3 arithmetic written out per channel in glm's evaluation order)
 __forceinline__ __device__ float3 computeColorFromSH(int idx, int deg, int max_coeffs, float3 pos,
-                                                     float3 campos, const float* shs,
+                                                     float3 campos, const float* shs, const float* shs_rest,
                                                      uint8_t* clamped_bits) {
   float3 dir = {pos.x - campos.x, pos.y - campos.y, pos.z - campos.z};
   float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
   dir.x = dir.x / len;
   dir.y = dir.y / len;
   dir.z = dir.z / len;
-  const float* sh = shs + (size_t)idx * max_coeffs * 3;
+  // coefficient k of channel c is sh0[c] for k = 0 and sh[3k + c] for k >= 1: one [P,M,3] tensor, or the DC part and
+  // coefficients 1..M-1 as two tensors (the -3 makes the same 3k + c index valid for the second tensor)
+  const float* sh0 = shs_rest ? shs + (size_t)idx * 3 : shs + (size_t)idx * max_coeffs * 3;
+  const float* sh = shs_rest ? shs_rest + (size_t)idx * (max_coeffs - 1) * 3 - 3 : sh0;
   float res[3];
 #pragma unroll
-  for (int c = 0; c < 3; c++) res[c] = SH_C0 * sh[c];
+  for (int c = 0; c < 3; c++) res[c] = SH_C0 * sh0[c];
   if (deg > 0) {
     float x = dir.x, y = dir.y, z = dir.z;
 #pragma unroll
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
   } else if (!a.render_depth_only) {
     float3 campos = {a.campos[0], a.campos[1], a.campos[2]};
     uint8_t bits;
-    feat = computeColorFromSH(idx, a.D, a.M, p_orig, campos, a.shs, &bits);
+    feat = computeColorFromSH(idx, a.D, a.M, p_orig, campos, a.shs, a.shs_rest, &bits);
     a.clamped[idx] = bits;
   }
 
@@ -256,6 +260,7 @@ int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, uint32_t* io
   a.rotations = f.rotations;
   a.opacities = f.opacities;
   a.shs = f.shs;
+  a.shs_rest = f.shs_rest;
   a.cov3D_precomp = f.cov3D_precomp;
   a.colors_precomp = f.colors_precomp;
   a.all_map = f.all_map;

@@ -27,6 +27,7 @@ struct PBArgs {
   const float* means3D;
   const int* radii;
   const float* shs;
+  const float* shs_rest;
   const uint8_t* clamped;
   const float* scales;
   const float* rotations;
@@ -37,7 +38,8 @@ struct PBArgs {
   float h_x, h_y, tan_fovx, tan_fovy;
   float half_w, half_h;
   uint32_t magic;  // floor(2^32 / (3M)) + 1: word index -> row by multiply-high
-  int vec_ok;      // shs and dL_dsh are 16-byte aligned
+  uint32_t magic_dc, magic_rest;  // the same for rows of 3 and 3(M-1) words (split SH tensors)
+  int vec_ok;      // the SH tensors and their gradients are 16-byte aligned
   const float* campos;
   const float4* arena;
   int has_all_map;
@@ -48,6 +50,7 @@ struct PBArgs {
   float* dL_dopacity;
   float* dL_dcov3D;
   float* dL_dsh;
+  float* dL_dsh_rest;
   float* dL_dscales;
   float* dL_drotations;
   float* dL_dall_map;
@@ -81,14 +84,15 @@ __forceinline__ __device__ void write_zero_row(const PBArgs& a, int idx) {
   for (int i = 0; i < 5; i++) p[i] = 0.f;
 }
 
-// warp-cooperative copy between the warp's [32][L] block of global rows (contiguous words, 16-byte aligned because
-// it starts at a multiple of 32 rows) and its shared-memory tile (row stride Ls = L|1 words).  The block is moved
-// as float4 (fully coalesced 512-byte requests); word i of the block belongs to row i / L, computed with a
-// multiply-high (`magic` = floor(2^32 / L) + 1, exact for i < 2^16).
+// warp-cooperative copy between a contiguous block of 32 global rows of `Lsrc` words (16-byte aligned because it
+// starts at a multiple of 32 rows) and columns [col0, col0 + Lsrc) of the warp's shared-memory tile (row stride Ls
+// words).  The block is moved as float4 (fully coalesced 512-byte requests); word i of the block belongs to row
+// i / Lsrc, computed with a multiply-high (`magic` = floor(2^32 / Lsrc) + 1, exact for i < 2^16).
 template <bool STORE>
-__device__ __forceinline__ void tile_copy(float* tile, float* gblock, int nwords, int L, int Ls, uint32_t magic,
-                                          bool vec_ok, int lane) {
-  const int pad = Ls - L;
+__device__ __forceinline__ void tile_copy(float* tile, float* gblock, int nwords, int Lsrc, int Ls, int col0,
+                                          uint32_t magic, bool vec_ok, int lane) {
+  const int pad = Ls - Lsrc;
+  tile += col0;
   // nwords is a multiple of 4 for a full block of 32 rows; the tail (and everything, if the caller's tensors are
   // not 16-byte aligned) goes through the scalar loop below
   const int nvec = vec_ok ? (nwords >> 2) : 0;
@@ -417,8 +421,18 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
   const bool visible = in_range && (a.radii[idx] > 0);
   const bool any_visible = __any_sync(0xffffffffu, visible);
   const bool has_sh = a.shs != nullptr;
+  // SH rows: one [P,M,3] tensor, or DC + coefficients 1..M-1 as two tensors (columns 0..2 and 3.. of the tile)
+  const bool split = a.shs_rest != nullptr;
+  const bool vec = a.vec_ok != 0;
   if (has_sh && any_visible) {
-    tile_copy<false>(tile, const_cast<float*>(a.shs) + row0 * L, rows * L, L, Ls, a.magic, a.vec_ok != 0, lane);
+    if (split) {
+      tile_copy<false>(tile, const_cast<float*>(a.shs) + row0 * 3, rows * 3, 3, Ls, 0, a.magic_dc, vec, lane);
+      if (L > 3)
+        tile_copy<false>(tile, const_cast<float*>(a.shs_rest) + row0 * (L - 3), rows * (L - 3), L - 3, Ls, 3,
+                         a.magic_rest, vec, lane);
+    } else {
+      tile_copy<false>(tile, const_cast<float*>(a.shs) + row0 * L, rows * L, L, Ls, 0, a.magic, vec, lane);
+    }
     __syncwarp();
   }
   if (visible) {
@@ -432,7 +446,13 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
   }
   if (has_sh) {
     __syncwarp();
-    tile_copy<true>(tile, a.dL_dsh + row0 * L, rows * L, L, Ls, a.magic, a.vec_ok != 0, lane);
+    if (split) {
+      tile_copy<true>(tile, a.dL_dsh + row0 * 3, rows * 3, 3, Ls, 0, a.magic_dc, vec, lane);
+      if (L > 3)
+        tile_copy<true>(tile, a.dL_dsh_rest + row0 * (L - 3), rows * (L - 3), L - 3, Ls, 3, a.magic_rest, vec, lane);
+    } else {
+      tile_copy<true>(tile, a.dL_dsh + row0 * L, rows * L, L, Ls, 0, a.magic, vec, lane);
+    }
   }
 }
 
@@ -447,6 +467,7 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.means3D = f.means3D;
   a.radii = f.radii;
   a.shs = f.shs;
+  a.shs_rest = f.shs_rest;
   a.clamped = g.clamped;
   a.scales = f.scales;
   a.rotations = f.rotations;
@@ -455,7 +476,9 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.view = f.view.viewmatrix;
   a.proj = f.view.projmatrix;
   a.magic = (a.M > 0) ? (uint32_t)(0x100000000ull / (uint64_t)(a.M * 3)) + 1u : 0u;
-  a.vec_ok = ((((uintptr_t)f.shs) | ((uintptr_t)f.dL_dsh)) & 15u) == 0;
+  a.magic_dc = (uint32_t)(0x100000000ull / 3ull) + 1u;
+  a.magic_rest = (a.M > 1) ? (uint32_t)(0x100000000ull / (uint64_t)((a.M - 1) * 3)) + 1u : 0u;
+  a.vec_ok = ((((uintptr_t)f.shs) | ((uintptr_t)f.dL_dsh) | ((uintptr_t)f.shs_rest) | ((uintptr_t)f.dL_dsh_rest)) & 15u) == 0;
   a.half_w = (float)(0.5 * f.view.image_width);
   a.half_h = (float)(0.5 * f.view.image_height);
   a.h_x = focal_x;
@@ -472,6 +495,7 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.dL_dopacity = f.dL_dopacity;
   a.dL_dcov3D = f.dL_dcov3D;
   a.dL_dsh = (f.shs != nullptr) ? f.dL_dsh : nullptr;
+  a.dL_dsh_rest = (f.shs != nullptr && f.shs_rest != nullptr) ? f.dL_dsh_rest : nullptr;
   a.dL_dscales = f.dL_dscales;
   a.dL_drotations = f.dL_drotations;
   a.dL_dall_map = f.dL_dall_map;

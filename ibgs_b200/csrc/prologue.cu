@@ -158,9 +158,8 @@ __global__ void __launch_bounds__(256) prologue_backward_kernel(const ProArgs a)
 
 int fill(ProArgs& p, const IbgsPrologueArgs& a) {
   if (a.P < 0 || a.sh_rest < 0) { ibgs_set_error("P and sh_rest must be >= 0"); return IBGS_EINVAL; }
-  if (!a.xyz || !a.opacity_raw || !a.scaling_raw || !a.rotation_raw || !a.features_dc ||
-      (a.sh_rest > 0 && !a.features_rest)) {
-    ibgs_set_error("xyz / opacity_raw / scaling_raw / rotation_raw / features_dc / features_rest must not be NULL");
+  if (!a.xyz || !a.opacity_raw || !a.scaling_raw || !a.rotation_raw) {
+    ibgs_set_error("xyz / opacity_raw / scaling_raw / rotation_raw must not be NULL");
     return IBGS_EINVAL;
   }
   if ((a.normal_raw != nullptr) != (a.offset != nullptr) ||
@@ -200,15 +199,17 @@ extern "C" int ibgs_prologue_forward(const IbgsPrologueArgs* a, void* stream_v) 
   int rc = fill(p, *a);
   if (rc != IBGS_OK) return rc;
   if (a->P == 0) return IBGS_OK;
-  if (!a->opacity || !a->scales || !a->rotations || !a->shs || (a->normal_raw && !a->all_map)) {
+  if (!a->opacity || !a->scales || !a->rotations || (a->normal_raw && !a->all_map)) {
     ibgs_set_error("output pointers must not be NULL");
     return IBGS_EINVAL;
   }
   if (!a->normal_raw) p.all_map = nullptr;
   prologue_forward_kernel<<<(a->P + 255) / 256, 256, 0, s>>>(p);
   KERNEL_CHECK(0, s);
-  sh_rows_kernel<false><<<copy_grid(p), 256, 0, s>>>(p);
-  KERNEL_CHECK(0, s);
+  if (a->shs) {  // NULL: the caller hands features_dc / features_rest to the rasterizer in place (shs_rest)
+    sh_rows_kernel<false><<<copy_grid(p), 256, 0, s>>>(p);
+    KERNEL_CHECK(0, s);
+  }
   return IBGS_OK;
 }
 
@@ -219,14 +220,18 @@ extern "C" int ibgs_prologue_backward(const IbgsPrologueArgs* a, void* stream_v)
   int rc = fill(p, *a);
   if (rc != IBGS_OK) return rc;
   if (a->P == 0) return IBGS_OK;
-  if (!a->d_opacity_raw || !a->d_scaling_raw || !a->d_rotation_raw || !a->d_features_dc ||
-      (a->sh_rest > 0 && !a->d_features_rest) || (a->normal_raw && (!a->d_normal_raw || !a->d_offset || !a->d_xyz))) {
+  const bool with_sh = a->d_features_dc != nullptr;  // NULL: SH gradients do not pass through the prologue
+  if (!a->d_opacity_raw || !a->d_scaling_raw || !a->d_rotation_raw ||
+      (with_sh && a->sh_rest > 0 && !a->d_features_rest) ||
+      (a->normal_raw && (!a->d_normal_raw || !a->d_offset || !a->d_xyz))) {
     ibgs_set_error("gradient output pointers must not be NULL");
     return IBGS_EINVAL;
   }
   prologue_backward_kernel<<<(a->P + 255) / 256, 256, 0, s>>>(p);
   KERNEL_CHECK(0, s);
-  sh_rows_kernel<true><<<copy_grid(p), 256, 0, s>>>(p);
-  KERNEL_CHECK(0, s);
+  if (with_sh) {
+    sh_rows_kernel<true><<<copy_grid(p), 256, 0, s>>>(p);
+    KERNEL_CHECK(0, s);
+  }
   return IBGS_OK;
 }

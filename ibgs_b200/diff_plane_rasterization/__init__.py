@@ -31,9 +31,9 @@ def cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, means2D_abs, sh, colors_precomp, opacities, scales, rotations,
-                        cov3Ds_precomp, all_map, raster_settings):
+                        cov3Ds_precomp, all_map, raster_settings, sh_rest=None):
     return _RasterizeGaussians.apply(means3D, means2D, means2D_abs, sh, colors_precomp, opacities, scales,
-                                     rotations, cov3Ds_precomp, all_map, raster_settings)
+                                     rotations, cov3Ds_precomp, all_map, raster_settings, sh_rest)
 
 
 def _ptr(t):
@@ -112,7 +112,7 @@ def _fill_view(view, rs, device, sh_coeffs, keep):
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, means2D_abs, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, all_maps, raster_settings):
+                cov3Ds_precomp, all_maps, raster_settings, sh_rest=None):
         rs = raster_settings
         if means3D.ndimension() != 2 or means3D.size(1) != 3:
             # rasterize_points.cu:69-71
@@ -125,6 +125,12 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         means3D_c = _f32c(means3D, device)
         sh_c = _f32c(sh, device)
+        # extension over the reference API: `sh` may hold only the DC coefficient [P,1,3] with coefficients 1..M-1 in
+        # their own tensor `sh_rest` [P,M-1,3] (GaussianModel stores them apart, scene/gaussian_model.py:139-143)
+        split_sh = sh_rest is not None and sh_rest.numel() != 0
+        sh_rest_c = _f32c(sh_rest, device) if split_sh else torch.empty(0, device=device)
+        if split_sh and (sh_c is None or sh_c.numel() == 0 or sh_c.size(1) != 1):
+            raise RuntimeError("shs_rest needs shs to be the [P,1,3] DC coefficients")
         colors_c = _f32c(colors_precomp, device)
         opac_c = _f32c(opacities, device)
         scales_c = _f32c(scales, device)
@@ -154,9 +160,12 @@ class _RasterizeGaussians(torch.autograd.Function):
         a = N.IbgsForwardArgs()
         a.P = P
         M_sh = sh_c.size(1) if (sh_c is not None and sh_c.numel() != 0) else 0
+        if split_sh:
+            M_sh = 1 + sh_rest_c.size(1)
         src_images_c, src_depths_c = _fill_view(a.view, rs, device, M_sh, keep)
         a.means3D = _ptr(means3D_c)
         a.shs = _ptr(sh_c)
+        a.shs_rest = _ptr(sh_rest_c) if split_sh else None
         a.colors_precomp = _ptr(colors_c)
         a.opacities = _ptr(opac_c)
         a.scales = _ptr(scales_c)
@@ -224,7 +233,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.view_keep = keep
         ctx.save_for_backward(out_normal_map, out_median_intersected_depth, out_warped_image, colors_c,
                               allmap_c, means3D_c, scales_c, rot_c, cov_c, radii, sh_c, geomBuffer,
-                              binningBuffer, imgBuffer)
+                              binningBuffer, imgBuffer, sh_rest_c)
         ctx.mark_non_differentiable(radii, out_use_first_src_frame)
         return (color, radii, out_normal_map, out_median_intersected_depth, out_cam_feat, out_warped_image,
                 out_min_depth_diff, out_camera_ray, out_use_first_src_frame)
@@ -236,11 +245,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         (normal_map_pixels, median_intersected_depth_pixels, warped_image_pixels, colors_precomp, all_maps,
          means3D, scales, rotations, cov3Ds_precomp, radii, sh, geomBuffer, binningBuffer,
-         imgBuffer) = ctx.saved_tensors
+         imgBuffer, sh_rest) = ctx.saved_tensors
+        split_sh = sh_rest.numel() != 0
         device = means3D.device
         P = means3D.size(0)
         H, W = int(rs.image_height), int(rs.image_width)
         M_sh = sh.size(1) if sh.numel() != 0 else 0
+        if split_sh:
+            M_sh = 1 + sh_rest.size(1)
         fopt = dict(dtype=torch.float32, device=device)
 
         def cot(g, shape):
@@ -265,7 +277,8 @@ class _RasterizeGaussians(torch.autograd.Function):
         dL_dopacity = torch.empty((P, 1), **fopt)
         need_cov = cov3Ds_precomp.numel() != 0
         dL_dcov3D = torch.empty((P, 6), **fopt) if need_cov else torch.zeros((0,), **fopt)
-        dL_dsh = torch.empty((P, M_sh, 3), **fopt)
+        dL_dsh = torch.empty((P, 1 if split_sh else M_sh, 3), **fopt)
+        dL_dsh_rest = torch.empty((P, M_sh - 1, 3), **fopt) if split_sh else None
         dL_dscales = torch.empty((P, 3), **fopt)
         dL_drotations = torch.empty((P, 4), **fopt)
 
@@ -278,6 +291,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             _fill_view(a.view, rs, device, M_sh, keep)
             a.means3D = _ptr(means3D)
             a.shs = _ptr(sh)
+            a.shs_rest = _ptr(sh_rest) if split_sh else None
             a.colors_precomp = _ptr(colors_precomp)
             a.scales = _ptr(scales)
             a.rotations = _ptr(rotations)
@@ -306,6 +320,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             a.dL_dopacity = dL_dopacity.data_ptr()
             a.dL_dcov3D = dL_dcov3D.data_ptr() if need_cov else None
             a.dL_dsh = dL_dsh.data_ptr() if M_sh else None
+            a.dL_dsh_rest = dL_dsh_rest.data_ptr() if split_sh else None
             a.dL_dscales = dL_dscales.data_ptr()
             a.dL_drotations = dL_drotations.data_ptr()
             a.dL_dall_map = dL_dall_map.data_ptr()
@@ -350,6 +365,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             dL_dcov3D if (need[8] and need_cov) else None,
             dL_dall_map if (need[9] and all_maps.numel()) else None,
             None,
+            dL_dsh_rest if (split_sh and len(need) > 11 and need[11]) else None,
         )
         return grads
 
@@ -401,7 +417,7 @@ class GaussianRasterizer(nn.Module):
         return visible
 
     def forward(self, means3D, means2D, means2D_abs, opacities, shs=None, colors_precomp=None, scales=None,
-                rotations=None, cov3D_precomp=None, all_map=None):
+                rotations=None, cov3D_precomp=None, all_map=None, shs_rest=None):
         raster_settings = self.raster_settings
 
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -424,5 +440,6 @@ class GaussianRasterizer(nn.Module):
         if all_map is None:
             all_map = torch.Tensor([])
 
+        # shs_rest (not in the reference API): shs = _features_dc, shs_rest = _features_rest, read in place
         return rasterize_gaussians(means3D, means2D, means2D_abs, shs, colors_precomp, opacities, scales,
-                                   rotations, cov3D_precomp, all_map, raster_settings)
+                                   rotations, cov3D_precomp, all_map, raster_settings, shs_rest)

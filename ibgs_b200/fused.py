@@ -31,7 +31,7 @@ def _c(t):
 class _GaussianPrologue(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, opacity_raw, scaling_raw, rotation_raw, features_dc, features_rest, normal_raw, offset,
-                world_view_transform, camera_center):
+                world_view_transform, camera_center, concat_sh=True):
         if not xyz.is_cuda:
             raise RuntimeError("ibgs_b200.fused: parameters must be CUDA tensors (there is no CPU path)")
         device = xyz.device
@@ -45,7 +45,7 @@ class _GaussianPrologue(torch.autograd.Function):
         opacity = torch.empty((P, 1), **fopt)
         scales = torch.empty((P, 3), **fopt)
         rotations = torch.empty((P, 4), **fopt)
-        shs = torch.empty((P, K1 + 1, 3), **fopt)
+        shs = torch.empty((P, K1 + 1, 3), **fopt) if concat_sh else None
         all_map = torch.empty((P, 5), **fopt) if with_map else None
         a = N.IbgsPrologueArgs()
         a.P, a.sh_rest = P, K1
@@ -54,22 +54,29 @@ class _GaussianPrologue(torch.autograd.Function):
         if with_map:
             a.normal_raw, a.offset = nrm.data_ptr(), off.data_ptr()
         a.world_view_transform, a.camera_center = view.data_ptr(), cam.data_ptr()
-        a.opacity, a.scales, a.rotations, a.shs = (opacity.data_ptr(), scales.data_ptr(), rotations.data_ptr(),
-                                                   shs.data_ptr())
+        a.opacity, a.scales, a.rotations = opacity.data_ptr(), scales.data_ptr(), rotations.data_ptr()
+        a.shs = shs.data_ptr() if concat_sh else None
         a.all_map = all_map.data_ptr() if with_map else None
         if P:
             with torch.cuda.device(device):
                 N.check(N.lib.ibgs_prologue_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream(device).cuda_stream)),
                         "ibgs_prologue_forward")
         ctx.with_map = with_map
+        ctx.concat_sh = concat_sh
         ctx.shapes = [tuple(t.shape) for t in (xyz, opacity_raw, scaling_raw, rotation_raw, features_dc, features_rest)]
         ctx.save_for_backward(*ins, *((nrm, off) if with_map else ()), view, cam)
+        outs = [opacity, scales, rotations]
+        if concat_sh:
+            outs.append(shs)
         if with_map:
-            return opacity, scales, rotations, shs, all_map
-        return opacity, scales, rotations, shs
+            outs.append(all_map)
+        return tuple(outs)
 
     @staticmethod
-    def backward(ctx, g_opacity, g_scales, g_rotations, g_shs, g_all_map=None):
+    def backward(ctx, g_opacity, g_scales, g_rotations, *rest):
+        rest = list(rest)
+        g_shs = rest.pop(0) if ctx.concat_sh else None
+        g_all_map = rest.pop(0) if ctx.with_map else None
         saved = ctx.saved_tensors
         xyz, opacity_raw, scaling_raw, rotation_raw, fdc, frest = saved[:6]
         with_map = ctx.with_map
@@ -80,8 +87,9 @@ class _GaussianPrologue(torch.autograd.Function):
         K1 = frest.size(1) if frest.numel() else 0
         keep = [None if g is None else _c(g) for g in (g_opacity, g_scales, g_rotations, g_shs, g_all_map)]
         d = {n: torch.empty_like(t) for n, t in (("opacity_raw", opacity_raw), ("scaling_raw", scaling_raw),
-                                                ("rotation_raw", rotation_raw), ("features_dc", fdc),
-                                                ("features_rest", frest))}
+                                                ("rotation_raw", rotation_raw))}
+        if ctx.concat_sh:
+            d.update(features_dc=torch.empty_like(fdc), features_rest=torch.empty_like(frest))
         if with_map:
             d.update(xyz=torch.empty_like(xyz), normal_raw=torch.empty_like(nrm), offset=torch.empty_like(off))
         a = N.IbgsPrologueArgs()
@@ -109,13 +117,15 @@ class _GaussianPrologue(torch.autograd.Function):
         return (out(0, "xyz"), out(1, "opacity_raw"), out(2, "scaling_raw"), out(3, "rotation_raw"),
                 out(4, "features_dc"), out(5, "features_rest"),
                 d["normal_raw"] if (with_map and need[6]) else None, d["offset"] if (with_map and need[7]) else None,
-                None, None)
+                None, None, None)
 
 
 def gaussian_prologue(xyz, opacity_raw, scaling_raw, rotation_raw, features_dc, features_rest, normal_raw=None,
-                      offset=None, world_view_transform=None, camera_center=None):
+                      offset=None, world_view_transform=None, camera_center=None, concat_sh=True):
     """Activated rasterizer inputs from the raw GaussianModel parameters; see the module docstring.
-    With normal_raw/offset = None no all_map is produced (4 outputs instead of 5)."""
+    With normal_raw/offset = None no all_map is produced (4 outputs instead of 5).  With concat_sh=False no `shs` is
+    produced either (the tuple is opacity, scales, rotations[, all_map]): pass features_dc / features_rest to the
+    rasterizer as `shs=` / `shs_rest=` and it reads them in place, which saves the torch.cat round trip per view."""
     if (normal_raw is None) != (offset is None):
         raise ValueError("normal_raw and offset must be given together")
     if normal_raw is not None and (world_view_transform is None or camera_center is None):
@@ -124,4 +134,4 @@ def gaussian_prologue(xyz, opacity_raw, scaling_raw, rotation_raw, features_dc, 
         world_view_transform = torch.eye(4, device=xyz.device)
         camera_center = torch.zeros(3, device=xyz.device)
     return _GaussianPrologue.apply(xyz, opacity_raw, scaling_raw, rotation_raw, features_dc, features_rest, normal_raw,
-                                   offset, world_view_transform, camera_center)
+                                   offset, world_view_transform, camera_center, concat_sh)

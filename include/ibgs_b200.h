@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IBGS_ABI_VERSION 1
+#define IBGS_ABI_VERSION 2
 
 /* Compile-time constants of the reference (cuda_rasterizer/config.h:15-19, auxiliary.h:21-23). */
 #define IBGS_NUM_CHANNELS 3
@@ -78,7 +78,10 @@ typedef struct IbgsForwardArgs {
   int32_t P;
   IbgsView view;
   const float* means3D;        /* [P,3] */
-  const float* shs;            /* [P,M,3] or NULL */
+  const float* shs;            /* [P,M,3] or NULL; with shs_rest given: the DC coefficient only, [P,1,3] */
+  const float* shs_rest;       /* NULL, or coefficients 1..M-1 as their own tensor [P,M-1,3] (GaussianModel keeps
+                                  _features_dc / _features_rest apart, scene/gaussian_model.py:139-143; reading them
+                                  in place saves the torch.cat the reference does per view) */
   const float* colors_precomp; /* [P,3] or NULL */
   const float* opacities;      /* [P] */
   const float* scales;         /* [P,3] or NULL */
@@ -111,7 +114,8 @@ typedef struct IbgsBackwardArgs {
   int64_t R;
   IbgsView view;
   const float* means3D;
-  const float* shs;
+  const float* shs;            /* as in the forward: [P,M,3], or the DC part when shs_rest is given */
+  const float* shs_rest;
   const float* colors_precomp;
   const float* scales;
   const float* rotations;
@@ -138,7 +142,8 @@ typedef struct IbgsBackwardArgs {
   float* dL_dcolors;      /* [P,3] */
   float* dL_dopacity;     /* [P,1] */
   float* dL_dcov3D;       /* [P,6] */
-  float* dL_dsh;          /* [P,M,3] or NULL */
+  float* dL_dsh;          /* [P,M,3] or NULL; with shs_rest given: [P,1,3] */
+  float* dL_dsh_rest;     /* [P,M-1,3] when shs_rest is given, else NULL */
   float* dL_dscales;      /* [P,3] */
   float* dL_drotations;   /* [P,4] */
   float* dL_dall_map;     /* [P,5] */
@@ -162,7 +167,9 @@ int ibgs_dist2(int32_t P, const float* points, float* mean_dists, void* scratch,
  * entry point).  Replaces the ~30 PyTorch kernels gaussian_renderer.render() runs over all Gaussians before every
  * rasterizer call: the activations of the GaussianModel getters (scene/gaussian_model.py:127-147), the learnt plane
  * normal (get_normal, :166-173) and the all_map construction (gaussian_renderer/__init__.py:304-315) -- and their
- * autograd backward.  normal_raw/offset may both be NULL (no all_map, e.g. colour-only renders).  In the backward
+ * autograd backward.  normal_raw/offset may both be NULL (no all_map, e.g. colour-only renders).  shs may be NULL
+ * (no concatenation: the caller passes features_dc / features_rest to ibgs_forward as shs / shs_rest), and likewise
+ * d_features_dc in the backward call.  In the backward
  * call every g_* may be NULL (= zero cotangent) and d_xyz holds only the all_map path's share of dL/dxyz. */
 typedef struct IbgsPrologueArgs {
   int32_t P;

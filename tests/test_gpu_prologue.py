@@ -84,3 +84,70 @@ def test_rasterizing_through_fused_prologue_equals_torch_prologue():
         grads.append({k: v.grad for k, v in leaves.items()})
     for k in IN:
         assert _rel(grads[0][k], grads[1][k]) <= 1e-3, (k, _rel(grads[0][k], grads[1][k]))
+
+
+@pytest.mark.parametrize("deg,P", [(2, None), (3, 2011), (1, 777)])
+def test_split_sh_tensors_equal_concatenated_path(deg, P):
+    """`shs=_features_dc, shs_rest=_features_rest` (read in place) must give bit-identical outputs, and the same SH
+    gradients, as the reference API's single concatenated tensor."""
+    from ibgs_b200 import synthetic as S
+    import ibgs_b200.diff_plane_rasterization as dpr
+    import ibgs_testutil as U
+    sc = U.scene_to_device(S.make_scene("cfg1" if P is None else "tiny", P=P, sh_degree=deg))
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    rs = U.make_settings(dpr, sc, render_geo=True, depth_error_threshold=0.05)
+    z = torch.zeros_like(sc["means3D"])
+    common = dict(means3D=sc["means3D"], means2D=z, means2D_abs=z, opacities=sc["opacities"], scales=sc["scales"],
+                  rotations=sc["rotations"], all_map=sc["all_map"])
+
+    def run(**sh_kw):
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sh_kw.items()}
+        res = dpr.GaussianRasterizer(rs)(**common, **leaves)
+        torch.autograd.backward([res[0], res[2], res[3], res[5]], [cot["color"], cot["normal"], cot["depth"], cot["warped"]])
+        return res, {k: v.grad for k, v in leaves.items()}
+
+    r1, g1 = run(shs=sc["shs"])
+    r2, g2 = run(shs=sc["shs"][:, :1].contiguous(), shs_rest=sc["shs"][:, 1:].contiguous())
+    for a, b in zip(r1, r2):
+        assert torch.equal(a, b)
+    # the SH gradient is a per-Gaussian function of dL/dcolour, which the tile renderer sums with float atomics:
+    # two runs agree to rounding, not bit for bit
+    assert _rel(g2["shs"], g1["shs"][:, :1]) <= 1e-4 and _rel(g2["shs_rest"], g1["shs"][:, 1:]) <= 1e-4
+    with pytest.raises(RuntimeError, match="DC"):
+        dpr.GaussianRasterizer(rs)(**common, shs=sc["shs"], shs_rest=sc["shs"][:, 1:].contiguous())
+
+
+def test_fused_prologue_without_sh_concat_end_to_end():
+    from ibgs_b200 import fused, synthetic as S
+    import ibgs_b200.diff_plane_rasterization as dpr
+    import ibgs_testutil as U
+    sc = U.scene_to_device(S.make_scene("cfg1"))
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
+    P = sc["P"]
+    raw = dict(xyz=sc["means3D"], opacity_raw=torch.logit(sc["opacities"].clamp(1e-4, 1 - 1e-4)).view(P, 1),
+               scaling_raw=sc["scales"].log(), rotation_raw=sc["rotations"] * 0.5,
+               fdc=sc["shs"][:, :1].contiguous(), frest=sc["shs"][:, 1:].contiguous(),
+               normal_raw=sc["normals_world"] * 2.0, offset=torch.zeros((P, 1), device="cuda"))
+    V, cam = sc["viewmatrix"], sc["campos"]
+    rs = U.make_settings(dpr, sc, render_geo=True)
+    z = torch.zeros_like(sc["means3D"])
+    out = []
+    for concat in (True, False):
+        leaves = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+        pro = fused.gaussian_prologue(*[leaves[k] for k in IN], V, cam, concat_sh=concat)
+        if concat:
+            opacity, scales, rotations, shs, all_map = pro
+            sh_kw = dict(shs=shs)
+        else:
+            opacity, scales, rotations, all_map = pro
+            sh_kw = dict(shs=leaves["fdc"], shs_rest=leaves["frest"])
+        res = dpr.GaussianRasterizer(rs)(means3D=leaves["xyz"], means2D=z, means2D_abs=z, opacities=opacity,
+                                         scales=scales, rotations=rotations, all_map=all_map, **sh_kw)
+        torch.autograd.backward([res[0], res[2], res[3], res[5]], [cot["color"], cot["normal"], cot["depth"], cot["warped"]])
+        out.append((res, {k: v.grad for k, v in leaves.items()}))
+    for a, b in zip(out[0][0], out[1][0]):
+        assert torch.equal(a, b)
+    for k in IN:
+        assert _rel(out[0][1][k], out[1][1][k]) <= 1e-4, k   # float atomics: run-to-run summation order

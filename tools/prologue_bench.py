@@ -14,13 +14,15 @@ g = torch.Generator().manual_seed(1)
 shapes = [(P, 1), (P, 3), (P, 4), (P, K, 3), (P, 5)]
 cots = [torch.randn(s, generator=g).cuda() for s in shapes]
 res = {}
-for name, fn in (("torch", PR.torch_prologue), ("fused", fused.gaussian_prologue)):
+def fused_nocat(*a):
+    return fused.gaussian_prologue(*a, concat_sh=False)
+for name, fn in (("torch", PR.torch_prologue), ("fused", fused.gaussian_prologue), ("fused_nocat", fused_nocat)):
     leaves = {k: p[k].clone().requires_grad_(True) for k in IN}
     def step():
         for v in leaves.values():
             v.grad = None
         outs = fn(*[leaves[k] for k in IN], p["V"], p["cam"])
-        torch.autograd.backward(list(outs), cots)
+        torch.autograd.backward(list(outs), cots if len(outs) == 5 else [cots[0], cots[1], cots[2], cots[4]])
     for _ in range(3):
         step()
     torch.cuda.synchronize()
@@ -35,5 +37,5 @@ for name, fn in (("torch", PR.torch_prologue), ("fused", fused.gaussian_prologue
 words_in = 3 + 1 + 3 + 4 + 3 * K + 3 + 1
 words_out = 1 + 3 + 4 + 3 * K + 5
 alg = 4 * P * (2 * words_in + 2 * words_out + words_in)   # fwd: in+out, bwd: in + cotangents + grads
-print(json.dumps({"P": P, "K": K, "torch_ms": res["torch"], "fused_ms": res["fused"], "speedup": res["torch"] / res["fused"],
+print(json.dumps({"P": P, "K": K, "torch_ms": res["torch"], "fused_ms": res["fused"], "fused_without_sh_concat_ms": res["fused_nocat"], "speedup": res["torch"] / res["fused"],
                   "fused_algorithmic_bytes": alg, "fused_GBps": alg / (res["fused"] * 1e-3) / 1e9}))

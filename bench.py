@@ -333,13 +333,18 @@ def prologue_timing(P, device, K=9, iters=10):
     g = torch.Generator().manual_seed(1)
     cots = [torch.randn(s, generator=g).to(device) for s in ((P, 1), (P, 3), (P, 4), (P, K, 3), (P, 5))]
     out = {}
-    for name, fn in (("torch", PR.torch_prologue), ("fused", fused.gaussian_prologue)):
+    def fused_nocat(*a):
+        return fused.gaussian_prologue(*a, concat_sh=False)
+
+    for name, fn in (("torch", PR.torch_prologue), ("fused", fused.gaussian_prologue),
+                     ("fused_without_sh_concat", fused_nocat)):
         leaves = {k: p[k].clone().requires_grad_(True) for k in names}
 
         def step():
             for v in leaves.values():
                 v.grad = None
-            torch.autograd.backward(list(fn(*[leaves[k] for k in names], p["V"], p["cam"])), cots)
+            outs = list(fn(*[leaves[k] for k in names], p["V"], p["cam"]))
+            torch.autograd.backward(outs, cots if len(outs) == 5 else [cots[0], cots[1], cots[2], cots[4]])
         for _ in range(3):
             step()
         torch.cuda.synchronize(device)

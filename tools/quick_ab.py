@@ -36,12 +36,29 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--geo", type=int, default=1)
+    ap.add_argument("--depth-only", action="store_true", help="time the depth-only forward (render.py's source-depth renders)")
     a = ap.parse_args()
     t0 = time.time()
     sc = U.scene_to_device(S.make_scene(a.name))
     sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
     cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
     print(f"scene {a.name}: P={sc['P']} {sc['W']}x{sc['H']} built in {time.time()-t0:.1f}s", flush=True)
+    if a.depth_only:
+        rs = U.make_settings(dpr, sc, render_geo=False, render_depth_only=True)
+        z = torch.zeros_like(sc["means3D"])
+
+        def ours_depth():
+            with torch.no_grad():
+                dpr.GaussianRasterizer(rs)(means3D=sc["means3D"], means2D=z, means2D_abs=z, opacities=sc["opacities"],
+                                           shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"], all_map=sc["all_map"])
+        t = timed(ours_depth, a.iters)
+        line = f"OURS  {a.name} depth-only forward {t:.3f} ms"
+        if not a.no_ref:
+            from oracle import ref_ext
+            tr = timed(lambda: ref_ext.forward(sc, render_geo=False, render_depth_only=True), a.iters)
+            line += f"   REF {tr:.3f} ms   speedup x{tr / t:.2f}"
+        print(line, flush=True)
+        return
     geo = bool(a.geo)
     rs = U.make_settings(dpr, sc, render_geo=geo)
     leaf = {k: sc[k].detach().clone().requires_grad_(True)

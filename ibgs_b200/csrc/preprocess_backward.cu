@@ -42,7 +42,6 @@ struct PBArgs {
   int vec_ok;      // the SH tensors and their gradients are 16-byte aligned
   const float* campos;
   const float4* arena;
-  int has_all_map;
   float* dL_dmeans3D;
   float* dL_dmeans2D;
   float* dL_dmeans2D_abs;
@@ -487,7 +486,6 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.tan_fovy = f.view.tanfovy;
   a.campos = f.view.campos;
   a.arena = arena;
-  a.has_all_map = f.all_map != nullptr;
   a.dL_dmeans3D = f.dL_dmeans3D;
   a.dL_dmeans2D = f.dL_dmeans2D;
   a.dL_dmeans2D_abs = f.dL_dmeans2D_abs;

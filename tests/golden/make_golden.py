@@ -5,7 +5,7 @@
 The reference ships no golden vectors; these fixtures are outputs of the reference
 itself on the deterministic `tiny` / `cfg1` synthetic scenes (ibgs_b200/synthetic.py), including the
 source-view depth maps (rendered with the reference's own depth-only pass).  tests/test_oracle_golden.py
-checks the CPU oracle against them without a GPU; tests/test_gpu_golden.py checks the CUDA path.
+checks the CPU oracle against them without a GPU; tests/test_gpu_oracle.py checks the CUDA path.
 """
 import os
 import sys

@@ -46,6 +46,9 @@ def parse():
     # the data-parallel step is a batch of 8 views per GPU (gradient accumulation) followed
     # by one all-reduce of the per-Gaussian gradient arena
     ap.add_argument("--views-per-step", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=1,
+                    help="CUDA streams the views of a step are spread over (front-end kernels of one view overlap the "
+                         "tile renderers of another)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -201,11 +204,17 @@ class RefRunner:
         return 0
 
 
+STREAMS = []
+
+
 def run_steps(runner, wl, steps, world, e2e=False, stager=None):
     """K steps; returns the last colour image's checksum tensor (device)."""
     loss = None
+    main = torch.cuda.current_stream(wl.device)
     for _ in range(steps):
         runner.arena.zero_()
+        for st in STREAMS:
+            st.wait_stream(main)
         for vi, cam in enumerate(wl.views):
             if e2e:
                 simg, sdep, cam_d = stager.fetch(vi)
@@ -214,9 +223,15 @@ def run_steps(runner, wl, steps, world, e2e=False, stager=None):
                 sc = wl.scene_for(cam2, simg, sdep)
             else:
                 sc = wl.scene_for(cam)
-            color = runner.view_fwd_bwd(sc)
+            if STREAMS and not e2e:
+                with torch.cuda.stream(STREAMS[vi % len(STREAMS)]):
+                    color = runner.view_fwd_bwd(sc)
+            else:
+                color = runner.view_fwd_bwd(sc)
             if e2e:
                 stager.release(vi)
+        for st in STREAMS:
+            main.wait_stream(st)
         if world > 1:
             runner.arena.all_reduce()
         if e2e:
@@ -398,6 +413,8 @@ def main():
         runner = OursRunner(wl)
         N.lib.ibgs_profile_enable(0 if os.environ.get("IBGS_BENCH_NOPROF") else 1)
 
+    if args.streams > 1 and args.impl == "b200":
+        STREAMS.extend(torch.cuda.Stream(device=device) for _ in range(args.streams))
     V = args.views_per_step
     # ---- device-resident arm ---------------------------------------------------------------------------
     sampler, spath = start_clock_sampler(local_rank) if (rank == 0 and not os.environ.get("IBGS_BENCH_NOCLOCK")) else (None, "")

@@ -71,12 +71,25 @@ class IbgsPrologueArgs(C.Structure):
         "d_normal_raw", "d_offset")]
 
 
+class IbgsDepthBatchArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("V", C.c_int32), ("image_height", C.c_int32), ("image_width", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("buffer_length", C.c_int32), ("prefiltered", C.c_int32), ("debug", C.c_int32),
+    ] + [(n, _fp) for n in (
+        "viewmatrices", "projmatrices", "means3D", "opacities", "scales", "rotations", "cov3D_precomp", "all_maps",
+        "normals", "offsets", "camera_centers", "out_depths", "radii")] + [
+        ("num_rendered", C.POINTER(C.c_int64)), ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p)]
+
+
+MAX_DEPTH_BATCH = 16
+
 EXPORTS = [
     "ibgs_forward", "ibgs_backward", "ibgs_mark_visible", "ibgs_dist2_scratch_bytes", "ibgs_dist2",
     "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
     "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
     "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
-    "ibgs_prologue_backward",
+    "ibgs_prologue_backward", "ibgs_forward_depth_batch",
 ]
 
 
@@ -121,6 +134,8 @@ def _load():
     for fn in (lib.ibgs_prologue_forward, lib.ibgs_prologue_backward):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(IbgsPrologueArgs), C.c_void_p]
+    lib.ibgs_forward_depth_batch.restype = C.c_int64
+    lib.ibgs_forward_depth_batch.argtypes = [C.POINTER(IbgsDepthBatchArgs), C.c_void_p]
     return lib
 
 

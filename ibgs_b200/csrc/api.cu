@@ -16,7 +16,7 @@ long long g_launch_count = 0;
 
 namespace {
 thread_local char g_err[1024] = "";
-int32_t* g_pinned_count = nullptr;  // pinned host word for the num_rendered read-back
+int32_t* g_pinned_count = nullptr;  // pinned host words for the num_rendered read-back (256 bytes)
 }  // namespace
 
 // ---- per-stage event timer -------------------------------------------------------------------------
@@ -210,7 +210,7 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
     if (rc != IBGS_OK) return rc;
   }
 
-  if (!g_pinned_count) CUDA_TRY(cudaHostAlloc((void**)&g_pinned_count, 64, cudaHostAllocDefault));
+  if (!g_pinned_count) CUDA_TRY(cudaHostAlloc((void**)&g_pinned_count, 256, cudaHostAllocDefault));
 
   // We do not know R yet: the first scratch request holds the P-sized depth-order state, the second one (once R
   // is known) the R-sized binning temporaries.  Both stay alive until the forward's last launch is enqueued.
@@ -248,6 +248,106 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
   if (rc != IBGS_OK) return rc;
 
   rc = launch_render_forward(*a, g, im, b, tex, focal_x, focal_y, grid, s);
+  if (rc != IBGS_OK) return rc;
+  return R;
+}
+
+// Batched depth-only forward: the V*P (view, Gaussian) items are binned as ONE list -- a single stable depth sort over
+// all items interleaves the views, the tile id of an instance carries its view (view * T + tile), and the stable tile
+// sort brings every (view, tile) list back into ascending depth order with ties in ascending Gaussian id, i.e. exactly
+// the list a separate ibgs_forward call of that view builds.
+extern "C" int64_t ibgs_forward_depth_batch(IbgsDepthBatchArgs* a, void* stream_v) {
+  cudaStream_t s = (cudaStream_t)stream_v;
+  if (!a) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
+  const int P = a->P, V = a->V;
+  if (P < 0) { ibgs_set_error("P must be >= 0"); return IBGS_EINVAL; }
+  if (V < 1 || V > IBGS_MAX_DEPTH_BATCH) {
+    ibgs_set_error("V must be in [1,%d], got %d", IBGS_MAX_DEPTH_BATCH, V);
+    return IBGS_EINVAL;
+  }
+  if (a->num_rendered) for (int v = 0; v < V; v++) a->num_rendered[v] = 0;
+  if (P == 0) return 0;  // like rasterize_points.cu:101-102: the caller's zero-filled outputs stay
+  if (a->image_width <= 0 || a->image_height <= 0) {
+    ibgs_set_error("image size must be positive, got %dx%d", a->image_width, a->image_height);
+    return IBGS_EINVAL;
+  }
+  if (a->buffer_length < 1 || a->buffer_length > MAX_BL) {
+    ibgs_set_error("buffer_length must be in [1,%d], got %d", MAX_BL, a->buffer_length);
+    return IBGS_EINVAL;
+  }
+  if (!a->viewmatrices || !a->projmatrices || !a->means3D || !a->opacities || !a->out_depths || !a->alloc) {
+    ibgs_set_error("viewmatrices / projmatrices / means3D / opacities / out_depths / alloc must not be NULL");
+    return IBGS_EINVAL;
+  }
+  if (!a->cov3D_precomp && (!a->scales || !a->rotations)) {
+    ibgs_set_error("provide scales+rotations or cov3D_precomp");
+    return IBGS_EINVAL;
+  }
+  if (!a->all_maps && (!a->normals || !a->camera_centers)) {
+    ibgs_set_error("provide all_maps, or normals + camera_centers");
+    return IBGS_EINVAL;
+  }
+  if ((int64_t)P * V > 0x7fffffffLL) {
+    ibgs_set_error("P*V = %lld exceeds the int32 item limit", (long long)P * V);
+    return IBGS_ELIMIT;
+  }
+  const int W = a->image_width, H = a->image_height;
+  const float focal_y = H / (2.0f * a->tanfovy);
+  const float focal_x = W / (2.0f * a->tanfovx);
+  dim3 grid((W + TILE - 1) / TILE, (H + TILE - 1) / TILE, 1);
+  const size_t T = (size_t)grid.x * grid.y;
+  const size_t items = (size_t)P * V;
+
+  // one scratch request for the item-sized state: records / depths / tiles_touched, radii (when the caller does not
+  // want them), tile ranges, per-view counters, depth-order state
+  GeomState g;
+  OrderState ord;
+  const size_t geom_bytes = carve_geom(g, nullptr, items);
+  const size_t order_bytes = carve_order(ord, nullptr, items);
+  const size_t radii_bytes = a->radii ? 0 : align_up(items * sizeof(int32_t), 256);
+  const size_t ranges_bytes = align_up(T * V * sizeof(uint2), 256);
+  const size_t counts_bytes = 256;
+  char* base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH,
+                               geom_bytes + order_bytes + radii_bytes + ranges_bytes + counts_bytes);
+  if (!base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  carve_geom(g, base, items);
+  carve_order(ord, base + geom_bytes, items);
+  int32_t* radii = a->radii ? a->radii : (int32_t*)(base + geom_bytes + order_bytes);
+  uint2* ranges = (uint2*)(base + geom_bytes + order_bytes + radii_bytes);
+  unsigned long long* counts = (unsigned long long*)(base + geom_bytes + order_bytes + radii_bytes + ranges_bytes);
+  static_assert(IBGS_MAX_DEPTH_BATCH * sizeof(unsigned long long) <= 256, "counter block");
+
+  if (!g_pinned_count) CUDA_TRY(cudaHostAlloc((void**)&g_pinned_count, 256, cudaHostAllocDefault));
+  CUDA_TRY(cudaMemsetAsync(counts, 0, counts_bytes, s));
+  COUNT_LAUNCH();
+  int rc = launch_preprocess_depth_batch(*a, g, radii, ord.iota, counts, focal_x, focal_y, grid, s);
+  if (rc != IBGS_OK) return rc;
+  rc = run_depth_order(g, ord, items, s);
+  if (rc != IBGS_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g_pinned_count, counts, V * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  unsigned long long R_u = 0;
+  for (int v = 0; v < V; v++) {
+    const unsigned long long rv = ((volatile unsigned long long*)g_pinned_count)[v];
+    if (a->num_rendered) a->num_rendered[v] = (int64_t)rv;
+    R_u += rv;
+  }
+  if (R_u > 0x7fffffffull) {
+    ibgs_set_error("num_rendered %llu over the %d views exceeds the int32 limit; render fewer views per call", R_u, V);
+    return IBGS_ELIMIT;
+  }
+  const int64_t R = (int64_t)R_u;
+
+  BinningState b;
+  ScratchState sc;
+  const size_t bin_bytes = carve_binning(b, nullptr, (size_t)R);
+  const size_t scratch_bytes = carve_scratch(sc, nullptr, (size_t)R, ibgs_sort_bits((int32_t)(T * V)) - 32);
+  char* base2 = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, bin_bytes + scratch_bytes);
+  if (!base2) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+  carve_binning(b, base2, (size_t)R);
+  rc = run_binning_items((int)items, radii, a->debug, V, g, ord, ranges, base2 + bin_bytes, scratch_bytes, b, R, grid, s);
+  if (rc != IBGS_OK) return rc;
+  rc = launch_render_depth_batch(*a, g, ranges, b, focal_x, focal_y, grid, s);
   if (rc != IBGS_OK) return rc;
   return R;
 }

@@ -32,17 +32,20 @@ struct GatherTiles {
 // One thread per position in depth order; one warp per 32 positions; rectangles with >= 8 tiles are written
 // cooperatively by the whole warp.  Tile order inside a rectangle is row-major like rasterizer_impl.cu:215-226
 // (irrelevant for the result -- a Gaussian appears at most once per tile -- but kept).
-template <typename TileT>
+// BATCH (ibgs_forward_depth_batch): the P items are (view, Gaussian) pairs, item id = view * items_per_view + Gaussian;
+// the tile id carries the view: view * tiles_per_view + tile.
+template <typename TileT, bool BATCH>
 __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32_t* __restrict__ order,
                                                              const uint32_t* __restrict__ tiles_touched,
                                                              const uint32_t* __restrict__ offsets,
                                                              const float4* __restrict__ rec,
                                                              const int* __restrict__ radii,
                                                              TileT* __restrict__ tile_ids,
-                                                             uint32_t* __restrict__ vals, dim3 grid) {
+                                                             uint32_t* __restrict__ vals, dim3 grid,
+                                                             uint32_t items_per_view, uint32_t tiles_per_view) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
-  uint32_t gid = 0, n = 0, off = 0;
+  uint32_t gid = 0, n = 0, off = 0, tbase = 0;
   uint2 rmin = {0, 0}, rmax = {0, 0};
   if (pos < P) {
     gid = order[pos];
@@ -52,6 +55,7 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
     off = (pos == 0) ? 0 : offsets[pos - 1];
     const float4 q0 = rec[4 * (size_t)gid];
     getRect(make_float2(q0.x, q0.y), radii[gid], rmin, rmax, grid);
+    if (BATCH) tbase = (gid / items_per_view) * tiles_per_view;
   }
   const uint32_t w = rmax.x - rmin.x;
   const bool big = n >= 8;
@@ -59,7 +63,7 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
     uint32_t o = off;
     for (uint32_t y = rmin.y; y < rmax.y; y++)
       for (uint32_t x = rmin.x; x < rmax.x; x++) {
-        tile_ids[o] = (TileT)(y * grid.x + x);
+        tile_ids[o] = (TileT)(tbase + y * grid.x + x);
         vals[o] = gid;
         o++;
       }
@@ -74,10 +78,11 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
     const uint32_t s_x0 = __shfl_sync(0xffffffffu, rmin.x, src);
     const uint32_t s_y0 = __shfl_sync(0xffffffffu, rmin.y, src);
     const uint32_t s_gid = __shfl_sync(0xffffffffu, gid, src);
+    const uint32_t s_tb = BATCH ? __shfl_sync(0xffffffffu, tbase, src) : 0u;
     for (uint32_t k = lane; k < s_n; k += 32) {
       const uint32_t y = s_y0 + k / s_w;
       const uint32_t x = s_x0 + k % s_w;
-      tile_ids[s_off + k] = (TileT)(y * grid.x + x);
+      tile_ids[s_off + k] = (TileT)(s_tb + y * grid.x + x);
       vals[s_off + k] = s_gid;
     }
   }
@@ -180,8 +185,17 @@ size_t carve_scratch(ScratchState& sc, char* base, size_t R, int tile_bits) {
 // steps 3-5
 int run_binning(const IbgsForwardArgs& a, const GeomState& g, const OrderState& o, const ImageState& im,
                 char* scratch_base, size_t scratch_bytes, BinningState& b, int64_t R, dim3 grid, cudaStream_t s) {
-  const int debug = a.view.debug;
-  const int tile_bits = ibgs_sort_bits((int32_t)(grid.x * grid.y)) - 32;
+  return run_binning_items(a.P, a.radii, a.view.debug, 1, g, o, im.ranges, scratch_base, scratch_bytes, b, R, grid, s);
+}
+
+// P items; with views > 1 they are (view, Gaussian) pairs (item id = view * P/views + Gaussian) and ranges has
+// views * tiles entries
+int run_binning_items(int P, const int* radii, int debug, int views, const GeomState& g, const OrderState& o,
+                      uint2* ranges, char* scratch_base, size_t scratch_bytes, BinningState& b, int64_t R, dim3 grid,
+                      cudaStream_t s) {
+  const uint32_t tiles_per_view = grid.x * grid.y;
+  const uint32_t items_per_view = (uint32_t)(P / views);
+  const int tile_bits = ibgs_sort_bits((int32_t)(tiles_per_view * views)) - 32;
   ScratchState sc;
   size_t need = carve_scratch(sc, scratch_base, (size_t)R, tile_bits);
   if (need > scratch_bytes) {
@@ -193,12 +207,16 @@ int run_binning(const IbgsForwardArgs& a, const GeomState& g, const OrderState& 
   uint16_t* t16_sorted = reinterpret_cast<uint16_t*>(sc.tiles_sorted);
   {
     ProfScope prof(PROF_DUPLICATE, s);
-    if (narrow)
-      emit_instances_kernel<uint16_t><<<(a.P + 255) / 256, 256, 0, s>>>(a.P, o.order, g.tiles_touched, o.offsets, g.rec,
-                                                                        a.radii, t16_unsorted, sc.vals_unsorted, grid);
-    else
-      emit_instances_kernel<uint32_t><<<(a.P + 255) / 256, 256, 0, s>>>(a.P, o.order, g.tiles_touched, o.offsets, g.rec,
-                                                                        a.radii, sc.tiles_unsorted, sc.vals_unsorted, grid);
+    const int nb = (P + 255) / 256;
+#define EMIT(T, BATCH, dst)                                                                                          \
+  emit_instances_kernel<T, BATCH><<<nb, 256, 0, s>>>(P, o.order, g.tiles_touched, o.offsets, g.rec, radii, dst,      \
+                                                     sc.vals_unsorted, grid, items_per_view, tiles_per_view)
+    if (views > 1) {
+      if (narrow) EMIT(uint16_t, true, t16_unsorted); else EMIT(uint32_t, true, sc.tiles_unsorted);
+    } else {
+      if (narrow) EMIT(uint16_t, false, t16_unsorted); else EMIT(uint32_t, false, sc.tiles_unsorted);
+    }
+#undef EMIT
     KERNEL_CHECK(debug, s);
   }
   if (R > 0) {
@@ -213,12 +231,12 @@ int run_binning(const IbgsForwardArgs& a, const GeomState& g, const OrderState& 
   }
   {
     ProfScope prof(PROF_RANGES, s);
-    CUDA_TRY(cudaMemsetAsync(im.ranges, 0, (size_t)grid.x * grid.y * sizeof(uint2), s));
+    CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)tiles_per_view * views * sizeof(uint2), s));
     if (R > 0) {
       if (narrow)
-        identify_tile_ranges_kernel<uint16_t><<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, t16_sorted, im.ranges);
+        identify_tile_ranges_kernel<uint16_t><<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, t16_sorted, ranges);
       else
-        identify_tile_ranges_kernel<uint32_t><<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, sc.tiles_sorted, im.ranges);
+        identify_tile_ranges_kernel<uint32_t><<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, sc.tiles_sorted, ranges);
       KERNEL_CHECK(debug, s);
     }
   }

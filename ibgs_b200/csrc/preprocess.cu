@@ -237,6 +237,130 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
   a.tiles_touched[idx] = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
 }
 
+// ---- batched depth-only preprocess (ibgs_forward_depth_batch) -------------------------------
+// One thread per Gaussian reads its parameters ONCE (the 3D covariance does not depend on the view) and then walks
+// the V views, writing the (view, Gaussian) item v*P + idx of every per-item array.  Per view the arithmetic is
+// preprocess_kernel's, operation for operation, so radii / depths / tiles_touched / records are bit-identical to V
+// separate depth-only calls given the same plane parameters.
+struct PreBatchArgs {
+  int P, V;
+  const float* means3D;
+  const float* scales;
+  float scale_modifier;
+  const float* rotations;
+  const float* opacities;
+  const float* cov3D_precomp;
+  const float* all_maps;
+  const float* normals;
+  const float* offsets;
+  const float* camera_centers;
+  const float* viewmatrices;
+  const float* projmatrices;
+  int W, H;
+  float tan_fovx, tan_fovy, focal_x, focal_y;
+  int* radii;
+  float4* rec;
+  float* depths;
+  uint32_t* tiles_touched;
+  uint32_t* iota;
+  unsigned long long* counts;
+  dim3 grid;
+  int prefiltered;
+};
+
+__global__ void __launch_bounds__(256) preprocess_depth_batch_kernel(const PreBatchArgs a) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = idx < a.P;
+  const int i = valid ? idx : 0;
+
+  const float3 p_orig = {a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]};
+  float cov3D[6];
+  if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[(size_t)i * 6 + k];
+  } else {
+    const float4 rot = reinterpret_cast<const float4*>(a.rotations)[i];
+    computeCov3D(a.scales[3 * (size_t)i], a.scales[3 * (size_t)i + 1], a.scales[3 * (size_t)i + 2], a.scale_modifier, rot,
+                 cov3D);
+  }
+  const float opacity = a.opacities[i];
+  const float tau = __logf(255.0f * opacity) + 0.02f;
+  float nrm[3] = {0.f, 0.f, 0.f};
+  float off = 0.f;
+  if (a.all_maps == nullptr) {
+    nrm[0] = a.normals[3 * (size_t)i]; nrm[1] = a.normals[3 * (size_t)i + 1]; nrm[2] = a.normals[3 * (size_t)i + 2];
+    if (a.offsets != nullptr) off = a.offsets[i];
+  }
+  const float pw[3] = {p_orig.x, p_orig.y, p_orig.z};
+
+  for (int v = 0; v < a.V; v++) {
+    const float* viewmatrix = a.viewmatrices + 16 * v;
+    const float* projmatrix = a.projmatrices + 16 * v;
+    const size_t o = (size_t)v * a.P + i;
+    uint32_t tiles = 0;
+    int radius_out = 0;
+    uint32_t depth_bits = 0xFFFFFFFFu;
+    do {
+      if (!valid) break;
+      const float3 p_view = transformPoint4x3(p_orig, viewmatrix);
+      if (p_view.z <= 0.2f) {
+        if (a.prefiltered) {
+          printf("Point is filtered although prefiltered is set. This shouldn't happen!");
+          __trap();
+        }
+        break;
+      }
+      const float4 p_hom = transformPoint4x4(p_orig, projmatrix);
+      const float p_w = 1.0f / (p_hom.w + 0.0000001f);
+      const float3 p_proj = {p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w};
+      const float3 cov = computeCov2D(p_orig, a.focal_x, a.focal_y, a.tan_fovx, a.tan_fovy, cov3D, viewmatrix);
+      const float det = (cov.x * cov.z - cov.y * cov.y);
+      if (det == 0.0f) break;
+      const float det_inv = 1.f / det;
+      const float3 conic = {cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv};
+      const float mid = 0.5f * (cov.x + cov.z);
+      const float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+      const float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+      const float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+      const float2 point_image = {ndc2Pix(p_proj.x, a.W), ndc2Pix(p_proj.y, a.H)};
+      uint2 rect_min, rect_max;
+      getRect(point_image, my_radius, rect_min, rect_max, a.grid);
+      const uint32_t area = (rect_max.x - rect_min.x) * (rect_max.y - rect_min.y);
+      if (area == 0) break;
+
+      float4 plane_n;
+      float plane_d;
+      if (a.all_maps != nullptr) {
+        const float* am = a.all_maps + o * 5;
+        plane_n = {am[0], am[1], am[2], 0.f};
+        plane_d = am[4];
+      } else {
+        const PlaneTerms t = plane_terms(nrm, off, pw, viewmatrix, a.camera_centers + 3 * v);
+        plane_n = {t.ln[0], t.ln[1], t.ln[2], 0.f};
+        plane_d = fabsf(t.u);
+      }
+      depth_bits = __float_as_uint(p_view.z);
+      radius_out = my_radius;
+      float4* rec = a.rec + 4 * o;
+      rec[0] = {point_image.x, point_image.y, conic.x, conic.y};
+      rec[1] = {conic.z, opacity, tau, 0.f};
+      rec[2] = {0.f, 0.f, 0.f, plane_d};
+      rec[3] = plane_n;
+      tiles = area;
+    } while (false);
+    if (valid) {
+      a.radii[o] = radius_out;
+      a.tiles_touched[o] = tiles;
+      a.iota[o] = (uint32_t)o;
+      reinterpret_cast<uint32_t*>(a.depths)[o] = depth_bits;
+    }
+    if (a.counts != nullptr) {
+      const uint32_t wsum = __reduce_add_sync(0xffffffffu, tiles);
+      if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(a.counts + v, (unsigned long long)wsum);
+    }
+  }
+}
+
 // reference rasterizer_impl.cu:171-183
 __global__ void mark_visible_kernel(int P, const float* means3D, const float* view, uint8_t* present) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -285,6 +409,44 @@ int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, uint32_t* io
   ProfScope prof(PROF_PREPROCESS, s);
   preprocess_kernel<<<(f.P + 255) / 256, 256, 0, s>>>(a);
   KERNEL_CHECK(f.view.debug, s);
+  return IBGS_OK;
+}
+
+int launch_preprocess_depth_batch(const IbgsDepthBatchArgs& f, const GeomState& g, int* radii, uint32_t* iota,
+                                  unsigned long long* counts, float focal_x, float focal_y, dim3 grid,
+                                  cudaStream_t s) {
+  PreBatchArgs a;
+  a.P = f.P;
+  a.V = f.V;
+  a.means3D = f.means3D;
+  a.scales = f.scales;
+  a.scale_modifier = f.scale_modifier;
+  a.rotations = f.rotations;
+  a.opacities = f.opacities;
+  a.cov3D_precomp = f.cov3D_precomp;
+  a.all_maps = f.all_maps;
+  a.normals = f.normals;
+  a.offsets = f.offsets;
+  a.camera_centers = f.camera_centers;
+  a.viewmatrices = f.viewmatrices;
+  a.projmatrices = f.projmatrices;
+  a.W = f.image_width;
+  a.H = f.image_height;
+  a.tan_fovx = f.tanfovx;
+  a.tan_fovy = f.tanfovy;
+  a.focal_x = focal_x;
+  a.focal_y = focal_y;
+  a.radii = radii;
+  a.rec = g.rec;
+  a.depths = g.depths;
+  a.tiles_touched = g.tiles_touched;
+  a.iota = iota;
+  a.counts = counts;
+  a.grid = grid;
+  a.prefiltered = f.prefiltered;
+  ProfScope prof(PROF_PREPROCESS, s);
+  preprocess_depth_batch_kernel<<<(f.P + 255) / 256, 256, 0, s>>>(a);
+  KERNEL_CHECK(f.debug, s);
   return IBGS_OK;
 }
 

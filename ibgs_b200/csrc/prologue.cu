@@ -24,36 +24,6 @@ struct ProArgs {
   uint32_t magic_limit;  // word indices below 2^32 / L divide exactly by multiply-high with `magic`
 };
 
-struct PlaneTerms {
-  float nh[3];    // normalised learnt normal
-  float inv_len;  // 1 / ||normal_raw||
-  float sgn;      // -1 if the normal was flipped towards the camera, else +1
-  float ng[3];    // sgn * nh
-  float ln[3];    // ng rotated into the camera frame
-  float u;        // signed plane distance in the camera frame (all_map[4] = |u|)
-};
-
-// scene/gaussian_model.py:166-173 + gaussian_renderer/__init__.py:306-311
-__device__ __forceinline__ PlaneTerms plane_terms(const float* n, float off, const float* p, const float* V,
-                                                  const float* cam) {
-  PlaneTerms t;
-  const float len = sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);  // torch.norm(dim=1)
-  t.inv_len = 1.0f / len;
-#pragma unroll
-  for (int i = 0; i < 3; i++) t.nh[i] = n[i] / len;
-  const float d = t.nh[0] * (cam[0] - p[0]) + t.nh[1] * (cam[1] - p[1]) + t.nh[2] * (cam[2] - p[2]);
-  t.sgn = (d < 0.0f) ? -1.0f : 1.0f;
-#pragma unroll
-  for (int i = 0; i < 3; i++) t.ng[i] = (d < 0.0f) ? -t.nh[i] : t.nh[i];
-  // local_normal = global_normal @ world_view_transform[:3,:3]   (V row-major 4x4)
-#pragma unroll
-  for (int j = 0; j < 3; j++) t.ln[j] = t.ng[0] * V[0 * 4 + j] + t.ng[1] * V[1 * 4 + j] + t.ng[2] * V[2 * 4 + j];
-  float gd = -(t.ng[0] * p[0] + t.ng[1] * p[1] + t.ng[2] * p[2]);
-  gd += off * t.sgn;  // offset_global = offset * (neg_mask*-2+1)
-  t.u = gd - (t.ln[0] * V[12] + t.ln[1] * V[13] + t.ln[2] * V[14]);
-  return t;
-}
-
 __global__ void __launch_bounds__(256) prologue_forward_kernel(const ProArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;

@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
   const int sub_x0 = blockIdx.x * TILE + (warp & 1) * 8;
   const int sub_y0 = blockIdx.y * TILE + (warp >> 1) * 4;
   const uint2 pix = {(unsigned)(sub_x0 + (lane & 7)), (unsigned)(sub_y0 + (lane >> 3))};
-  const uint32_t pix_id = W * pix.y + pix.x;
+  // blockIdx.z = view of a batched depth-only launch (0 otherwise): its tile ranges and output plane follow view z-1's
+  const uint32_t pix_id = (MODE == MODE_DEPTH ? blockIdx.z * (uint32_t)(W * H) : 0u) + W * pix.y + pix.x;
   const float2 pixf = {(float)pix.x, (float)pix.y};
   const float2 ray = {(pixf.x - a.cx) / a.focal_x, (pixf.y - a.cy) / a.focal_y};  // forward.cu:352
   const bool inside = pix.x < (unsigned)W && pix.y < (unsigned)H;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
   const float wx0 = (float)sub_x0, wx1 = (float)(sub_x0 + 7);
   const float wy0 = (float)sub_y0, wy1 = (float)(sub_y0 + 3);
 
-  const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
+  const uint2 range = a.ranges[((MODE == MODE_DEPTH ? blockIdx.z * gridDim.y : 0u) + blockIdx.y) * gridDim.x + blockIdx.x];
   const int total = (int)(range.y - range.x);
 
   if (MODE == MODE_GEO) {
@@ -259,8 +260,10 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
 
   if (!inside) return;
   const int HW = H * W;
-  a.final_T[pix_id] = T;
-  a.n_contrib[pix_id] = last_contributor;
+  if (MODE != MODE_DEPTH || a.final_T != nullptr) {  // the batched depth launch keeps no image state
+    a.final_T[pix_id] = T;
+    a.n_contrib[pix_id] = last_contributor;
+  }
 
   if (MODE != MODE_DEPTH) {
 #pragma unroll
@@ -471,5 +474,27 @@ int launch_render_forward(const IbgsForwardArgs& f, const GeomState& g, const Im
   }
   if (rc != IBGS_OK) return rc;
   KERNEL_CHECK(f.view.debug, s);
+  return IBGS_OK;
+}
+
+// ibgs_forward_depth_batch: V depth-only views in one launch (gridDim.z = V); ranges has V * tiles entries, rec holds
+// the V * P (view, Gaussian) records, out_depths is [V,1,H,W].
+int launch_render_depth_batch(const IbgsDepthBatchArgs& f, const GeomState& g, const uint2* ranges,
+                              const BinningState& b, float focal_x, float focal_y, dim3 grid, cudaStream_t s) {
+  FwdArgs fa = {};
+  fa.ranges = ranges;
+  fa.point_list = b.point_list;
+  fa.rec = g.rec;
+  fa.W = f.image_width;
+  fa.H = f.image_height;
+  fa.focal_x = focal_x;
+  fa.focal_y = focal_y;
+  fa.cx = float(fa.W * 0.5f);
+  fa.cy = float(fa.H * 0.5f);
+  fa.out_depth = f.out_depths;
+  ProfScope prof(PROF_RENDER_FWD, s);
+  int rc = dispatch_bl<MODE_DEPTH>(f.buffer_length, dim3(grid.x, grid.y, (unsigned)f.V), s, fa);
+  if (rc != IBGS_OK) return rc;
+  KERNEL_CHECK(f.debug, s);
   return IBGS_OK;
 }

@@ -199,6 +199,44 @@ typedef struct IbgsPrologueArgs {
 int ibgs_prologue_forward(const IbgsPrologueArgs* args, void* stream);
 int ibgs_prologue_backward(const IbgsPrologueArgs* args, void* stream);
 
+/* Batched source-view depth renders (optional fast path, the reference has no such
+ * entry point).  At test time and with do_render_src_depth the reference renders the plane depth of every source
+ * view with its own rasterizer call (gaussian_renderer/__init__.py:245-253 -> render_depth :33-145, i.e. V x
+ * [per-view all_map torch ops + preprocess + sort + depth-only render] over the SAME Gaussians).  This entry point
+ * renders V views (same image size and intrinsics) in ONE pass: one preprocess launch reads each Gaussian once and
+ * writes V records, the V*P (view, Gaussian) items go through ONE depth-order sort / scan / emission / tile sort
+ * with the view folded into the tile id, and one depth-only tile-renderer launch with gridDim.z = V.  Results per
+ * view are those of ibgs_forward with render_depth_only=1 (radii, tile lists and the blend order are bit-identical).
+ * Plane parameters: either all_maps [V,P,5] (what render_depth builds per view, :123-132), or -- all_maps NULL --
+ * the world-space normals [P,3] (un-normalised _normal, or the unit shortest axis) and optional offsets [P] plus the
+ * V camera centres, from which the kernel derives each view's (local normal, 1, |local distance|) itself
+ * (scene/gaussian_model.py:158-173 + gaussian_renderer/__init__.py:123-129). */
+#define IBGS_MAX_DEPTH_BATCH 16
+typedef struct IbgsDepthBatchArgs {
+  int32_t P, V;
+  int32_t image_height, image_width;
+  float tanfovx, tanfovy, scale_modifier;
+  int32_t buffer_length, prefiltered, debug;
+  const float* viewmatrices;   /* [V,16] */
+  const float* projmatrices;   /* [V,16] */
+  const float* means3D;        /* [P,3] */
+  const float* opacities;      /* [P] */
+  const float* scales;         /* [P,3] or NULL */
+  const float* rotations;      /* [P,4] or NULL */
+  const float* cov3D_precomp;  /* [P,6] or NULL */
+  const float* all_maps;       /* [V,P,5] or NULL */
+  const float* normals;        /* [P,3] world space; used when all_maps is NULL */
+  const float* offsets;        /* [P] or NULL */
+  const float* camera_centers; /* [V,3]; used when all_maps is NULL */
+  float* out_depths;           /* [V,1,H,W] */
+  int32_t* radii;              /* [V,P] or NULL */
+  int64_t* num_rendered;       /* HOST [V] or NULL: tile instances per view */
+  ibgs_alloc_fn alloc;         /* SCRATCH only */
+  void* alloc_user;
+} IbgsDepthBatchArgs;
+/* returns the total number of tile instances over the V views */
+int64_t ibgs_forward_depth_batch(IbgsDepthBatchArgs* args, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds; used by bench.py's e2e arm):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages
  * through its own device arena (cudaMallocAsync) and copies results back before returning. */

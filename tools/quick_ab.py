@@ -37,12 +37,78 @@ def main():
     ap.add_argument("--no-ref", action="store_true")
     ap.add_argument("--geo", type=int, default=1)
     ap.add_argument("--depth-only", action="store_true", help="time the depth-only forward (render.py's source-depth renders)")
+    ap.add_argument("--depth-batch", type=int, default=0, metavar="V",
+                    help="time V source-view depth renders: V single calls vs one ibgs_forward_depth_batch call")
     a = ap.parse_args()
     t0 = time.time()
     sc = U.scene_to_device(S.make_scene(a.name))
     sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
     cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
     print(f"scene {a.name}: P={sc['P']} {sc['W']}x{sc['H']} built in {time.time()-t0:.1f}s", flush=True)
+    if a.depth_batch:
+        import ibgs_b200.depth_batch as DB
+        V = a.depth_batch
+        cams = []
+        for i in range(V):
+            cam = S.src_view(sc, i % sc["nb_src"])
+            cams.append({k: (v.cuda() if torch.is_tensor(v) else v) for k, v in cam.items()})
+        st = DB.DepthBatchSettings(sc["H"], sc["W"], sc["tanfovx"], sc["tanfovy"], 1.0,
+                                   torch.stack([c["viewmatrix"] for c in cams]), torch.stack([c["projmatrix"] for c in cams]), 4)
+        centers = torch.stack([c["campos"] for c in cams])
+        all_maps = torch.stack([c["all_map"] for c in cams]).contiguous()
+        rss = [U.make_settings(dpr, sc, render_geo=False, render_depth_only=True, cam=c) for c in cams]
+        z = torch.zeros_like(sc["means3D"])
+
+        def torch_all_map(cam):   # render_depth's per-view plane parameters (gaussian_renderer/__init__.py:119-132)
+            return S.all_map_for_view(sc["means3D"], sc["normals_world"], cam["viewmatrix"], cam["campos"])
+
+        def singles(with_maps):
+            with torch.no_grad():
+                outs = []
+                for c, rs in zip(cams, rss):
+                    am = torch_all_map(c) if with_maps else c["all_map"]
+                    outs.append(dpr.GaussianRasterizer(rs)(means3D=sc["means3D"], means2D=z, means2D_abs=z,
+                                                           opacities=sc["opacities"], shs=sc["shs"], scales=sc["scales"],
+                                                           rotations=sc["rotations"], all_map=am)[3])
+                return torch.stack(outs)
+
+        def batch_maps():
+            return DB.render_depth_batch(st, sc["means3D"], sc["opacities"], scales=sc["scales"],
+                                         rotations=sc["rotations"], all_maps=all_maps)
+
+        def batch_fused():
+            return DB.render_depth_batch(st, sc["means3D"], sc["opacities"], scales=sc["scales"],
+                                         rotations=sc["rotations"], normals=sc["normals_world"], camera_centers=centers)
+
+        same = torch.equal(singles(False), batch_maps())
+        err = (batch_fused() - batch_maps()).abs().max().item()
+        t1 = timed(lambda: singles(False), a.iters)
+        t1m = timed(lambda: singles(True), a.iters)
+        t2 = timed(batch_maps, a.iters)
+        t3 = timed(batch_fused, a.iters)
+        print(f"OURS  {a.name} {V} source-depth renders: {V} calls {t1:.3f} ms ({t1m:.3f} ms with the torch all_map ops)  "
+              f"one batch call {t2:.3f} ms (given all_maps) / {t3:.3f} ms (plane terms in-kernel)   "
+              f"bit-identical={same} fused-vs-maps max|d|={err:.2e}", flush=True)
+        from ibgs_b200 import _native as N
+        N.lib.ibgs_profile_enable(1)
+        N.lib.ibgs_profile_reset()
+        for _ in range(5):
+            batch_fused()
+        torch.cuda.synchronize()
+        print("   batch stages (ms per call): " + "  ".join(f"{k} {ms / 5:.3f}" for k, (ms, n) in N.profile_read().items() if n),
+              f"  pixels differing > 1e-4 fused-vs-maps: {((batch_fused() - batch_maps()).abs() > 1e-4).float().mean().item():.2e}", flush=True)
+        N.lib.ibgs_profile_enable(0)
+        if not a.no_ref:
+            from oracle import ref_ext
+
+            def ref_singles():
+                for c in cams:
+                    am = torch_all_map(c)
+                    ref_ext.forward(sc, render_geo=False, render_depth_only=True, cam=dict(c, all_map=am))
+            tr = timed(ref_singles, a.iters)
+            print(f"REF   {a.name} {V} source-depth renders (torch all_map + rasterizer per view): {tr:.3f} ms   "
+                  f"speedup x{tr / t3:.2f}", flush=True)
+        return
     if a.depth_only:
         rs = U.make_settings(dpr, sc, render_geo=False, render_depth_only=True)
         z = torch.zeros_like(sc["means3D"])

@@ -377,6 +377,48 @@ def prologue_timing(P, device, K=9, iters=10):
     return out
 
 
+def depth_batch_timing(wl, iters=10):
+    """SURVEY.md section 8f rank 2 (next row, reported beside the headline, not part of it): the source-view depth
+    renders of one test view (gaussian_renderer/__init__.py:245-253) -- V rasterizer calls, each behind the torch
+    all_map construction, vs ONE ibgs_forward_depth_batch call that derives the plane terms in-kernel."""
+    import ibgs_b200.depth_batch as DB
+    S, U, dpr, sc, dev = wl.S, wl.U, wl.dpr, wl.sc, wl.device
+    cams = []
+    for i in range(sc["nb_src"]):
+        cam = S.src_view(sc, i)
+        cams.append({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in cam.items()})
+    st = DB.DepthBatchSettings(sc["H"], sc["W"], sc["tanfovx"], sc["tanfovy"], 1.0,
+                               torch.stack([c["viewmatrix"] for c in cams]),
+                               torch.stack([c["projmatrix"] for c in cams]), 4)
+    centers = torch.stack([c["campos"] for c in cams])
+    rss = [U.make_settings(dpr, sc, render_geo=False, render_depth_only=True, cam=c) for c in cams]
+    z = torch.zeros_like(sc["means3D"])
+
+    def singles():
+        with torch.no_grad():
+            for c, rs in zip(cams, rss):
+                am = S.all_map_for_view(sc["means3D"], sc["normals_world"], c["viewmatrix"], c["campos"])
+                dpr.GaussianRasterizer(rs)(means3D=sc["means3D"], means2D=z, means2D_abs=z, opacities=sc["opacities"],
+                                           shs=sc["shs"], scales=sc["scales"], rotations=sc["rotations"], all_map=am)
+
+    def batch():
+        DB.render_depth_batch(st, sc["means3D"], sc["opacities"], scales=sc["scales"], rotations=sc["rotations"],
+                              normals=sc["normals_world"], camera_centers=centers)
+
+    out = {"views": len(cams)}
+    for name, fn in (("per_view_calls_ms", singles), ("one_batch_call_ms", batch)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        out[name] = sorted(ts)[len(ts) // 2]
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -512,6 +554,16 @@ def main():
     elif args.gpus == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
     if args.impl == "b200" and args.gpus == 1:
+        try:
+            line["source_depth_batch"] = depth_batch_timing(wl)
+        except Exception as ex:  # extra information only: never lose the headline line over it
+            line["source_depth_batch"] = {"error": repr(ex)}
+        try:  # one SSIM loss term (forward+backward) at the workload's resolution
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ssim_bench
+            line["loss_ssim"] = ssim_bench.measure(wl.H, wl.W, iters=10, peak_gbs=peak_gbs)
+        except Exception as ex:
+            line["loss_ssim"] = {"error": repr(ex)}
         try:
             del runner
             torch.cuda.empty_cache()

@@ -82,6 +82,12 @@ class IbgsDepthBatchArgs(C.Structure):
         ("num_rendered", C.POINTER(C.c_int64)), ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p)]
 
 
+class IbgsSsimArgs(C.Structure):
+    _fields_ = [("planes", C.c_int32), ("height", C.c_int32), ("width", C.c_int32)] + [(k, _fp) for k in (
+        "img1", "img2", "ssim_map", "dm_dmu1", "dm_de11", "dm_de12", "dm_dmu2", "dL_dmap")] + [
+        ("dL_dmap_is_scalar", C.c_int32), ("dL_dmap_scale", C.c_float), ("dL_dimg1", _fp), ("dL_dimg2", _fp)]
+
+
 MAX_DEPTH_BATCH = 16
 
 EXPORTS = [
@@ -89,7 +95,7 @@ EXPORTS = [
     "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
     "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
     "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
-    "ibgs_prologue_backward", "ibgs_forward_depth_batch",
+    "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward",
 ]
 
 
@@ -134,6 +140,9 @@ def _load():
     for fn in (lib.ibgs_prologue_forward, lib.ibgs_prologue_backward):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(IbgsPrologueArgs), C.c_void_p]
+    for fn in (lib.ibgs_ssim_forward, lib.ibgs_ssim_backward):
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(IbgsSsimArgs), C.c_void_p]
     lib.ibgs_forward_depth_batch.restype = C.c_int64
     lib.ibgs_forward_depth_batch.argtypes = [C.POINTER(IbgsDepthBatchArgs), C.c_void_p]
     return lib

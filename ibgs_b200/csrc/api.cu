@@ -30,7 +30,8 @@ bool g_prof_is_open[PROF_COUNT] = {false};
 double g_prof_ms[PROF_COUNT] = {0};
 long long g_prof_n[PROF_COUNT] = {0};
 const char* g_prof_names[PROF_COUNT] = {"preprocess", "depth_order_sort", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
-                                        "texture_fill", "render_forward", "render_backward", "preprocess_backward"};
+                                        "texture_fill", "render_forward", "render_backward", "preprocess_backward",
+                                        "ssim_forward", "ssim_backward"};
 void prof_drain() {
   for (auto& p : g_prof_pending) {
     float ms = 0.f;

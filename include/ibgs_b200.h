@@ -237,6 +237,33 @@ typedef struct IbgsDepthBatchArgs {
 /* returns the total number of tile instances over the V views */
 int64_t ibgs_forward_depth_batch(IbgsDepthBatchArgs* args, void* stream);
 
+/* Fused SSIM map + backward (the loss step next to the rasterizer; optional fast path).
+ * Replaces utils/loss_utils.py:34-65 (ssim / _ssim), :67-90 (compute_photometric_ssim) and :92-117 (ssim2): the five
+ * depthwise 11x11 Gaussian-window convolutions (sigma 1.5, zero padding 5) and the SSIM formula with C1 = 0.01^2,
+ * C2 = 0.03^2, for `planes` independent H x W planes (batch and channels folded; the window is depthwise).
+ * The forward optionally stores the partial derivatives of the map with respect to the convolution outputs
+ * (mu1, e11 = W*img1^2, e12 = W*img1*img2; and mu2 for a differentiable img2 -- dm/de22 equals dm/de11); the backward turns them and the
+ * map's cotangent into dL_dimg1
+ * (and dL_dimg2 when given). */
+typedef struct IbgsSsimArgs {
+  int32_t planes, height, width;
+  const float* img1;      /* [planes,H,W] */
+  const float* img2;      /* [planes,H,W] */
+  float* ssim_map;        /* [planes,H,W] forward output */
+  float* dm_dmu1;         /* [planes,H,W] forward outputs / backward inputs; all NULL = inference */
+  float* dm_de11;
+  float* dm_de12;
+  float* dm_dmu2;         /* NULL unless img2 needs a gradient */
+  const float* dL_dmap;   /* backward: [planes,H,W]; or ONE device float broadcast to every pixel when
+                             dL_dmap_is_scalar (the `.mean()` case, no host read-back needed); or NULL (= 1) */
+  int32_t dL_dmap_is_scalar;
+  float dL_dmap_scale;    /* backward: multiplies dL_dmap */
+  float* dL_dimg1;        /* backward output [planes,H,W] */
+  float* dL_dimg2;        /* backward output or NULL */
+} IbgsSsimArgs;
+int ibgs_ssim_forward(const IbgsSsimArgs* args, void* stream);
+int ibgs_ssim_backward(const IbgsSsimArgs* args, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds; used by bench.py's e2e arm):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages
  * through its own device arena (cudaMallocAsync) and copies results back before returning. */

@@ -564,6 +564,11 @@ def main():
             line["loss_ssim"] = ssim_bench.measure(wl.H, wl.W, iters=10, peak_gbs=peak_gbs)
         except Exception as ex:
             line["loss_ssim"] = {"error": repr(ex)}
+        try:  # the optimizer step over the eight per-Gaussian parameter groups
+            import adam_bench
+            line["optimizer_step"] = adam_bench.measure(wl.P, iters=10, peak_gbs=peak_gbs)
+        except Exception as ex:
+            line["optimizer_step"] = {"error": repr(ex)}
         try:
             del runner
             torch.cuda.empty_cache()

@@ -88,6 +88,19 @@ class IbgsSsimArgs(C.Structure):
         ("dL_dmap_is_scalar", C.c_int32), ("dL_dmap_scale", C.c_float), ("dL_dimg1", _fp), ("dL_dimg2", _fp)]
 
 
+ADAM_MAX_GROUPS = 16
+
+
+class IbgsAdamGroup(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("count", C.c_int64), ("lr", C.c_float)]
+
+
+class IbgsAdamArgs(C.Structure):
+    _fields_ = [("params", _fp), ("grads", _fp), ("exp_avg", _fp), ("exp_avg_sq", _fp), ("num_groups", C.c_int32),
+                ("groups", IbgsAdamGroup * ADAM_MAX_GROUPS), ("beta1", C.c_float), ("beta2", C.c_float),
+                ("eps", C.c_float), ("step", C.c_int64), ("grad_scale", C.c_float), ("zero_grads", C.c_int32)]
+
+
 MAX_DEPTH_BATCH = 16
 
 EXPORTS = [
@@ -95,7 +108,7 @@ EXPORTS = [
     "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
     "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
     "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
-    "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward",
+    "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward", "ibgs_adam_step",
 ]
 
 
@@ -143,6 +156,8 @@ def _load():
     for fn in (lib.ibgs_ssim_forward, lib.ibgs_ssim_backward):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(IbgsSsimArgs), C.c_void_p]
+    lib.ibgs_adam_step.restype = C.c_int
+    lib.ibgs_adam_step.argtypes = [C.POINTER(IbgsAdamArgs), C.c_void_p]
     lib.ibgs_forward_depth_batch.restype = C.c_int64
     lib.ibgs_forward_depth_batch.argtypes = [C.POINTER(IbgsDepthBatchArgs), C.c_void_p]
     return lib

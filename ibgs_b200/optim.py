@@ -1,0 +1,102 @@
+"""One-launch Adam over flat arenas -- optional fast path for
+`gaussians.optimizer.step(); gaussians.optimizer.zero_grad()` (train.py:422-424).
+
+The reference builds `torch.optim.Adam(l, lr=0.0, eps=1e-15)` over eight per-Gaussian parameter groups with their own
+learning rates (scene/gaussian_model.py:227-240) and reschedules two of them every iteration through
+`optimizer.param_groups` (:251-262).  `ArenaAdam` keeps that surface -- `param_groups` is a list of dicts with `name`,
+`lr` and `params` -- but lays parameters, gradients and both moments out as four flat float32 arenas of one layout, so
+that (1) the data-parallel exchange is one all-reduce of the gradient arena (ibgs_b200/parallel.py) and (2) the update
+is one CUDA launch that touches every value once (`ibgs_adam_step`, csrc/adam.cu).  The parameters handed back are
+`torch.nn.Parameter` views into the arena whose `.grad` are views into the gradient arena: autograd accumulates into
+them in place.
+
+Densification replaces every per-Gaussian tensor and its optimizer state (scene/gaussian_model.py:362-596); after it,
+build a new ArenaAdam from the new tensors with `ArenaAdam.from_state(...)` carrying the moments over.
+There is no CPU or PyTorch fallback: CUDA tensors only.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import torch
+
+from . import _native as N
+
+
+class ArenaAdam:
+    def __init__(self, named_tensors, lrs, betas=(0.9, 0.999), eps=1e-15, exp_avg=None, exp_avg_sq=None, step=0):
+        """named_tensors: ordered {name: initial value (CUDA float32 tensor)}; lrs: {name: learning rate}."""
+        named_tensors = OrderedDict(named_tensors)
+        if not (1 <= len(named_tensors) <= N.ADAM_MAX_GROUPS):
+            raise ValueError(f"1..{N.ADAM_MAX_GROUPS} parameter groups, got {len(named_tensors)}")
+        first = next(iter(named_tensors.values()))
+        if not first.is_cuda:
+            raise RuntimeError("ibgs_b200.optim: parameters must be CUDA tensors (there is no CPU path)")
+        self.device = first.device
+        sizes = [int(t.numel()) for t in named_tensors.values()]
+        total = sum(sizes)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.flat_params = torch.empty(total, **f32)
+        self.flat_grads = torch.zeros(total, **f32)
+        self.exp_avg = torch.zeros(total, **f32)
+        self.exp_avg_sq = torch.zeros(total, **f32)
+        self.betas, self.eps, self.step_count = (float(betas[0]), float(betas[1])), float(eps), int(step)
+        self.params, self.grads, self.param_groups, self._ranges = OrderedDict(), OrderedDict(), [], OrderedDict()
+        off = 0
+        for (name, t), n in zip(named_tensors.items(), sizes):
+            sl = slice(off, off + n)
+            self.flat_params[sl].copy_(t.detach().reshape(-1))
+            p = torch.nn.Parameter(self.flat_params[sl].view(t.shape), requires_grad=True)
+            p.grad = self.flat_grads[sl].view(t.shape)
+            self.params[name], self.grads[name] = p, p.grad
+            self._ranges[name] = (off, n)
+            self.param_groups.append({"params": [p], "lr": float(lrs[name]), "name": name})
+            if exp_avg is not None and name in exp_avg:
+                self.exp_avg[sl].copy_(exp_avg[name].reshape(-1))
+                self.exp_avg_sq[sl].copy_(exp_avg_sq[name].reshape(-1))
+            off += n
+
+    @classmethod
+    def from_state(cls, named_tensors, lrs, exp_avg, exp_avg_sq, step, betas=(0.9, 0.999), eps=1e-15):
+        """Rebuild after densification / pruning from the new per-group tensors and their carried-over moments."""
+        return cls(named_tensors, lrs, betas=betas, eps=eps, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq, step=step)
+
+    def state(self, name):
+        off, n = self._ranges[name]
+        shape = self.params[name].shape
+        return {"step": self.step_count, "exp_avg": self.exp_avg[off:off + n].view(shape),
+                "exp_avg_sq": self.exp_avg_sq[off:off + n].view(shape)}
+
+    def all_reduce_grads(self, async_op=False):
+        """Sum of the gradient arena over ranks: one collective."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.all_reduce(self.flat_grads, op=dist.ReduceOp.SUM, async_op=async_op)
+        return None
+
+    def zero_grad(self, set_to_none=False):
+        # the gradients stay views into the arena (set_to_none would detach them from it): always zero in place
+        self.flat_grads.zero_()
+        for name, p in self.params.items():
+            if p.grad is None or p.grad.data_ptr() != self.grads[name].data_ptr():
+                p.grad = self.grads[name]
+
+    def step(self, grad_scale=1.0, zero_grads=False):
+        """One Adam update of every group with its current `param_groups[i]['lr']`; with zero_grads the gradient arena
+        is cleared in the same pass (step + zero_grad of train.py:422-424 in one launch)."""
+        for name, p in self.params.items():
+            if p.grad is None or p.grad.data_ptr() != self.grads[name].data_ptr():
+                raise RuntimeError(f"ArenaAdam: .grad of '{name}' no longer aliases the gradient arena "
+                                   "(use zero_grad() of this class, not set_to_none)")
+        self.step_count += 1
+        a = N.IbgsAdamArgs()
+        a.params, a.grads = self.flat_params.data_ptr(), self.flat_grads.data_ptr()
+        a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
+        a.num_groups = len(self.param_groups)
+        for i, g in enumerate(self.param_groups):
+            off, n = self._ranges[g["name"]]
+            a.groups[i].offset, a.groups[i].count, a.groups[i].lr = off, n, float(g["lr"])
+        a.beta1, a.beta2, a.eps = self.betas[0], self.betas[1], self.eps
+        a.step, a.grad_scale, a.zero_grads = self.step_count, float(grad_scale), int(bool(zero_grads))
+        with torch.cuda.device(self.device):
+            N.check(N.lib.ibgs_adam_step(C.byref(a), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
+                    "ibgs_adam_step")

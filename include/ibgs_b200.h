@@ -264,6 +264,29 @@ typedef struct IbgsSsimArgs {
 int ibgs_ssim_forward(const IbgsSsimArgs* args, void* stream);
 int ibgs_ssim_backward(const IbgsSsimArgs* args, void* stream);
 
+/* One-launch Adam step over flat arenas (optional fast path).  Replaces
+ * gaussians.optimizer.step() + zero_grad (train.py:422-424) for torch.optim.Adam(l, lr=0.0, eps=1e-15) with the eight
+ * per-Gaussian parameter groups of scene/gaussian_model.py:227-240: params / grads / exp_avg / exp_avg_sq are four flat
+ * float arrays of one layout, every group a contiguous [offset, offset+count) range with its own learning rate.
+ * Arithmetic: torch/optim/adam.py (amsgrad=False, weight_decay=0, maximize=False).  `step` is the 1-based count of this
+ * update (torch increments state['step'] before using it).  grad_scale multiplies the gradients first (1/views for a
+ * mean over a view batch); zero_grads != 0 clears the gradients in the same pass. */
+#define IBGS_ADAM_MAX_GROUPS 16
+typedef struct IbgsAdamGroup { int64_t offset, count; float lr; } IbgsAdamGroup;
+typedef struct IbgsAdamArgs {
+  float* params;
+  float* grads;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int32_t num_groups;
+  IbgsAdamGroup groups[IBGS_ADAM_MAX_GROUPS];
+  float beta1, beta2, eps;
+  int64_t step;
+  float grad_scale;
+  int32_t zero_grads;
+} IbgsAdamArgs;
+int ibgs_adam_step(const IbgsAdamArgs* args, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds; used by bench.py's e2e arm):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages
  * through its own device arena (cudaMallocAsync) and copies results back before returning. */

@@ -100,18 +100,40 @@ __device__ __forceinline__ void vertical_pass(const float (*hs)[SS_SY][SS_BX], c
   }
 }
 
+// Staging: warp w takes staged rows w, w+8, ...; a lane takes columns lane and 32+lane (the latter only for the 10 halo
+// columns + 6 zero columns of the padded pitch) -- no per-element division.  All global loads of the tile are issued
+// before the first shared-memory store (two fully unrolled phases): with the loads inside one rolled loop the CTA
+// paid a dependent global round trip per iteration.
 template <int NA, typename Load>
 __device__ __forceinline__ void stage_tiles(float (*raw)[SS_SY][SS_SXP], int x0, int y0, int W, int H, Load load) {
-  for (int i = threadIdx.x; i < SS_SY * SS_SXP; i += blockDim.x) {
-    const int row = i / SS_SXP, col = i - row * SS_SXP;
-    const int gx = x0 - SS_R + col, gy = y0 - SS_R + row;
-    const bool in = col < SS_BX + 2 * SS_R && gx >= 0 && gx < W && gy >= 0 && gy < H;  // zero padding (conv2d padding=5)
-    float v[NA];
+  constexpr int RIT = (SS_SY + 7) / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float v[RIT][2][NA];
 #pragma unroll
-    for (int a = 0; a < NA; a++) v[a] = 0.f;
-    if (in) load((size_t)gy * W + gx, v);
+  for (int it = 0; it < RIT; it++) {
+    const int row = warp + 8 * it;
+    const int gy = y0 - SS_R + row;
+    const bool row_ok = row < SS_SY && gy >= 0 && gy < H;   // zero padding (conv2d padding=5)
 #pragma unroll
-    for (int a = 0; a < NA; a++) raw[a][row][col] = v[a];
+    for (int h = 0; h < 2; h++) {
+      const int col = lane + 32 * h;
+      const int gx = x0 - SS_R + col;
+      const bool in = row_ok && col < SS_BX + 2 * SS_R && gx >= 0 && gx < W;
+#pragma unroll
+      for (int a = 0; a < NA; a++) v[it][h][a] = 0.f;
+      if (in) load((size_t)gy * W + gx, v[it][h]);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < RIT; it++) {
+    const int row = warp + 8 * it;
+    if (row < SS_SY) {
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        raw[a][row][lane] = v[it][0][a];
+        if (lane < SS_SXP - 32) raw[a][row][32 + lane] = v[it][1][a];
+      }
+    }
   }
 }
 
@@ -146,13 +168,16 @@ __global__ void __launch_bounds__(256) ssim_forward_kernel(const SsimArgs a) {
     const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
     const float s1 = res[2][r] - mu1_sq, s2 = res[3][r] - mu2_sq, s12 = res[4][r] - mu12;
     const float A = 2.f * mu12 + C1, B = 2.f * s12 + C2, Cc = mu1_sq + mu2_sq + C1, D = s1 + s2 + C2;
-    const float m = (A * B) / (Cc * D);   // loss_utils.py:60
+    // loss_utils.py:60.  Two approximate reciprocals (MUFU.RCP, ~1 ulp) replace the four IEEE divisions of the
+    // straightforward form: the map and its partials stay within a few ulp, far inside the 2e-5 / 1e-4 gates.
+    const float inv_C = __fdividef(1.f, Cc), inv_D = __fdividef(1.f, D);
+    const float inv_CD = inv_C * inv_D;
+    const float m = (A * B) * inv_CD;
     a.map[o] = m;
     if (PART >= 1) {
       // partials of m with respect to the convolution outputs mu1, e11 = W*x^2, e12 = W*xy (and mu2, e22), with
       // sigma1^2 = e11 - mu1^2, sigma12 = e12 - mu1 mu2 substituted
-      const float inv_CD = 1.f / (Cc * D);
-      const float m_Cc = m / Cc, m_D = m / D;
+      const float m_Cc = m * inv_C, m_D = m * inv_D;
       const float dB = 2.f * A * inv_CD;          // dm/de12 (= 2 * dm/dB)
       a.p_e11[o] = -m_D;
       a.p_e12[o] = dB;

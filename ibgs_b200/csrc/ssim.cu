@@ -100,40 +100,40 @@ __device__ __forceinline__ void vertical_pass(const float (*hs)[SS_SY][SS_BX], c
   }
 }
 
-// Staging: warp w takes staged rows w, w+8, ...; a lane takes columns lane and 32+lane (the latter only for the 10 halo
-// columns + 6 zero columns of the padded pitch) -- no per-element division.  All global loads of the tile are issued
-// before the first shared-memory store (two fully unrolled phases): with the loads inside one rolled loop the CTA
-// paid a dependent global round trip per iteration.
+// Staging: thread t takes elements t, t+256, ... of the [42][48] staged tile; (row, col) advance incrementally
+// (256 = 5*48 + 16), so there is one division per thread, not one per element.  All global loads of the tile are
+// issued before the first shared-memory store (two fully unrolled phases): with the loads inside one rolled loop the
+// CTA paid a dependent global round trip per iteration.
 template <int NA, typename Load>
 __device__ __forceinline__ void stage_tiles(float (*raw)[SS_SY][SS_SXP], int x0, int y0, int W, int H, Load load) {
-  constexpr int RIT = (SS_SY + 7) / 8;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float v[RIT][2][NA];
+  constexpr int ITERS = (SS_SY * SS_SXP + 255) / 256;
+  static_assert(256 % SS_SXP == 16 && 256 / SS_SXP == 5, "incremental (row, col) update below");
+  float v[ITERS][NA];
+  const int row0 = threadIdx.x / SS_SXP, col0 = threadIdx.x - row0 * SS_SXP;
+  int row = row0, col = col0;
 #pragma unroll
-  for (int it = 0; it < RIT; it++) {
-    const int row = warp + 8 * it;
-    const int gy = y0 - SS_R + row;
-    const bool row_ok = row < SS_SY && gy >= 0 && gy < H;   // zero padding (conv2d padding=5)
+  for (int it = 0; it < ITERS; it++) {
+    const int gx = x0 - SS_R + col, gy = y0 - SS_R + row;
+    // zero padding (conv2d padding=5); columns 42..47 of the padded pitch are zero as well
+    const bool in = row < SS_SY && col < SS_BX + 2 * SS_R && gx >= 0 && gx < W && gy >= 0 && gy < H;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int col = lane + 32 * h;
-      const int gx = x0 - SS_R + col;
-      const bool in = row_ok && col < SS_BX + 2 * SS_R && gx >= 0 && gx < W;
-#pragma unroll
-      for (int a = 0; a < NA; a++) v[it][h][a] = 0.f;
-      if (in) load((size_t)gy * W + gx, v[it][h]);
-    }
+    for (int a = 0; a < NA; a++) v[it][a] = 0.f;
+    if (in) load((size_t)gy * W + gx, v[it]);
+    col += 16;
+    row += 5;
+    if (col >= SS_SXP) { col -= SS_SXP; row += 1; }
   }
+  row = row0;
+  col = col0;
 #pragma unroll
-  for (int it = 0; it < RIT; it++) {
-    const int row = warp + 8 * it;
+  for (int it = 0; it < ITERS; it++) {
     if (row < SS_SY) {
 #pragma unroll
-      for (int a = 0; a < NA; a++) {
-        raw[a][row][lane] = v[it][0][a];
-        if (lane < SS_SXP - 32) raw[a][row][32 + lane] = v[it][1][a];
-      }
+      for (int a = 0; a < NA; a++) raw[a][row][col] = v[it][a];
     }
+    col += 16;
+    row += 5;
+    if (col >= SS_SXP) { col -= SS_SXP; row += 1; }
   }
 }
 
@@ -191,13 +191,25 @@ __global__ void __launch_bounds__(256) ssim_forward_kernel(const SsimArgs a) {
 
 // BOTH: also the gradient with respect to img2
 template <bool BOTH>
-__global__ void __launch_bounds__(256) ssim_backward_kernel(const SsimArgs a) {
+__global__ void __launch_bounds__(256, 4) ssim_backward_kernel(const SsimArgs a) {
   constexpr int NA = BOTH ? 4 : 3;
   extern __shared__ __align__(16) float ssim_smem[];
   auto raw = reinterpret_cast<float(*)[SS_SY][SS_SXP]>(ssim_smem);
   auto hs = reinterpret_cast<float(*)[SS_SY][SS_BX]>(ssim_smem + NA * SS_SY * SS_SXP);
   const int x0 = blockIdx.x * SS_BX, y0 = blockIdx.y * SS_BY;
   const size_t plane = (size_t)blockIdx.z * a.H * a.W;
+  // this thread's own pixels of both images are needed only by the last statement: request them first
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int gx = x0 + tx;
+  float xv[4], yv[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int gy = y0 + 4 * ty + r;
+    const bool in = gx < a.W && gy < a.H;
+    const size_t o = plane + (size_t)gy * a.W + gx;
+    xv[r] = in ? a.img1[o] : 0.f;
+    yv[r] = in ? a.img2[o] : 0.f;
+  }
   const float gs = (a.g && a.g_scalar) ? a.g[0] * a.g_scale : a.g_scale;
   const float* gmap = (a.g && !a.g_scalar) ? a.g + plane : nullptr;
   stage_tiles<NA>(raw, x0, y0, a.W, a.H, [&](size_t o, float* v) {
@@ -213,17 +225,15 @@ __global__ void __launch_bounds__(256) ssim_backward_kernel(const SsimArgs a) {
     for (int i = 0; i < NA; i++) out[i] = in[i];
   });
   __syncthreads();
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   float res[NA][4];
   vertical_pass<NA>(hs, a.win, tx, ty, res);
-  const int gx = x0 + tx;
   if (gx >= a.W) return;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const int gy = y0 + 4 * ty + r;
     if (gy >= a.H) break;
     const size_t o = plane + (size_t)gy * a.W + gx;
-    const float x = a.img1[o], y = a.img2[o];
+    const float x = xv[r], y = yv[r];
     a.d_img1[o] = res[0][r] + 2.f * x * res[1][r] + y * res[2][r];
     if (BOTH) a.d_img2[o] = res[3][r] + 2.f * y * res[1][r] + x * res[2][r];
   }

@@ -21,7 +21,7 @@ def _declared_functions():
 def test_library_exports_every_declared_symbol():
     from ibgs_b200 import _native as N
     names = _declared_functions()
-    assert len(names) >= 13
+    assert len(names) >= 24
     for n in names:
         assert hasattr(N.lib, n), f"{n} declared in include/ibgs_b200.h but not exported"
     assert sorted(N.EXPORTS) == names
@@ -30,17 +30,34 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header(tmp_path):
     from ibgs_b200 import _native as N
+    probes = [("sizeof(IbgsView)", C.sizeof(N.IbgsView)), ("sizeof(IbgsForwardArgs)", C.sizeof(N.IbgsForwardArgs)),
+              ("sizeof(IbgsBackwardArgs)", C.sizeof(N.IbgsBackwardArgs)),
+              ("offsetof(IbgsForwardArgs, alloc)", N.IbgsForwardArgs.alloc.offset),
+              ("offsetof(IbgsBackwardArgs, dL_dmeans3D)", N.IbgsBackwardArgs.dL_dmeans3D.offset),
+              ("offsetof(IbgsView, bg)", N.IbgsView.bg.offset),
+              ("sizeof(IbgsPrologueArgs)", C.sizeof(N.IbgsPrologueArgs)),
+              ("offsetof(IbgsPrologueArgs, d_offset)", N.IbgsPrologueArgs.d_offset.offset),
+              ("sizeof(IbgsDepthBatchArgs)", C.sizeof(N.IbgsDepthBatchArgs)),
+              ("offsetof(IbgsDepthBatchArgs, viewmatrices)", N.IbgsDepthBatchArgs.viewmatrices.offset),
+              ("offsetof(IbgsDepthBatchArgs, num_rendered)", N.IbgsDepthBatchArgs.num_rendered.offset),
+              ("offsetof(IbgsDepthBatchArgs, alloc_user)", N.IbgsDepthBatchArgs.alloc_user.offset),
+              ("sizeof(IbgsSsimArgs)", C.sizeof(N.IbgsSsimArgs)),
+              ("offsetof(IbgsSsimArgs, dL_dmap_scale)", N.IbgsSsimArgs.dL_dmap_scale.offset),
+              ("offsetof(IbgsSsimArgs, dL_dimg2)", N.IbgsSsimArgs.dL_dimg2.offset),
+              ("sizeof(IbgsAdamGroup)", C.sizeof(N.IbgsAdamGroup)), ("sizeof(IbgsAdamArgs)", C.sizeof(N.IbgsAdamArgs)),
+              ("offsetof(IbgsAdamArgs, groups)", N.IbgsAdamArgs.groups.offset),
+              ("offsetof(IbgsAdamArgs, step)", N.IbgsAdamArgs.step.offset),
+              ("offsetof(IbgsAdamArgs, zero_grads)", N.IbgsAdamArgs.zero_grads.offset),
+              ("IBGS_MAX_DEPTH_BATCH", N.MAX_DEPTH_BATCH), ("IBGS_ADAM_MAX_GROUPS", N.ADAM_MAX_GROUPS),
+              ("IBGS_MAX_SRC", N.MAX_SRC), ("IBGS_MAX_BUFFER_LENGTH", N.MAX_BUFFER_LENGTH)]
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ibgs_b200.h"\n'
-                    'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(IbgsView), sizeof(IbgsForwardArgs),'
-                    ' sizeof(IbgsBackwardArgs), offsetof(IbgsForwardArgs, alloc), offsetof(IbgsBackwardArgs, dL_dmeans3D),'
-                    ' offsetof(IbgsView, bg));return 0;}\n')
+    body = "".join(f'printf("%zu\\n", (size_t)({expr}));' for expr, _ in probes)
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ibgs_b200.h"\nint main(){' + body + 'return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [C.sizeof(N.IbgsView), C.sizeof(N.IbgsForwardArgs), C.sizeof(N.IbgsBackwardArgs),
-            N.IbgsForwardArgs.alloc.offset, N.IbgsBackwardArgs.dL_dmeans3D.offset, N.IbgsView.bg.offset]
-    assert got == want
+    for (expr, want), g in zip(probes, got):
+        assert g == want, (expr, g, want)
 
 
 def test_sort_bits_follow_getHigherMsb():

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libibgs_b200.so")
+# IBGS_B200_LIB selects another build of the SAME library (kernel experiments, tools/build_variant.py); there is still no fallback
+LIB_PATH = os.environ.get("IBGS_B200_LIB") or os.path.join(_HERE, "_lib", "libibgs_b200.so")
 
 IBGS_BUF_GEOM, IBGS_BUF_BINNING, IBGS_BUF_IMAGE, IBGS_BUF_SCRATCH = 0, 1, 2, 3
 MAX_SRC = 5

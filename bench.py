@@ -51,6 +51,7 @@ def parse():
                          "tile renderers of another)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the extra whole-training-step timing (N = 1)")
     return ap.parse_args()
 
 
@@ -419,6 +420,98 @@ def depth_batch_timing(wl, iters=10):
     return out
 
 
+def train_step_timing(wl, impl, steps=4, warmup=3):
+    """One whole training step around the rasterizer, per view (extra key, N = 1): raw GaussianModel parameters ->
+    per-view prologue -> render_geo rasterizer -> image loss (L1 + SSIM, train.py:302-305) + multi-view photometric
+    loss over the 4 warped source images (L1 + SSIM map, train.py:318-336) + a normal / depth term -> backward;
+    every 8 views one Adam step over the eight parameter groups + zero_grad (train.py:422-424).
+    impl "b200": every stage through this repo (fused prologue without the SH concat, split-SH rasterizer, fused SSIM,
+    one-launch ArenaAdam).  impl "reference": the reference's way (its torch expressions for prologue and SSIM, its
+    unmodified CUDA rasterizer, torch.optim.Adam).  The colour-aggregation network is not part of either."""
+    import prologue_ref as PR
+    S, U, sc, dev = wl.S, wl.U, wl.sc, wl.device
+    P = wl.P
+    op = sc["opacities"].clamp(1e-4, 1 - 1e-4)
+    raw = {"xyz": sc["means3D"].clone(), "f_dc": sc["shs"][:, :1, :].contiguous(), "f_rest": sc["shs"][:, 1:, :].contiguous(),
+           "opacity": torch.log(op / (1 - op)), "scaling": torch.log(sc["scales"]), "rotation": sc["rotations"].clone(),
+           "normal": sc["normals_world"].clone(), "offset": torch.zeros((P, 1), device=dev)}
+    lrs = {"xyz": 1.6e-4, "f_dc": 0.0025, "f_rest": 0.0025 / 20, "opacity": 0.05, "scaling": 0.005, "rotation": 0.001,
+           "normal": 0.001, "offset": 1.6e-5}
+    g = torch.Generator().manual_seed(5)
+    gt = torch.rand((3, wl.H, wl.W), generator=g).to(dev)
+    nref = torch.nn.functional.normalize(torch.randn((3, wl.H, wl.W), generator=g), dim=0).to(dev)
+    Vn = len(wl.views)
+    if impl == "b200":
+        from ibgs_b200.fused import gaussian_prologue
+        from ibgs_b200.loss_utils import ssim, compute_photometric_ssim
+        from ibgs_b200.optim import ArenaAdam
+        opt = ArenaAdam(raw, lrs)
+        pr = opt.params
+        z = torch.zeros((P, 3), device=dev)
+
+        def render(cam, scv):
+            opacity, scales, rotations, all_map = gaussian_prologue(
+                pr["xyz"], pr["opacity"], pr["scaling"], pr["rotation"], pr["f_dc"], pr["f_rest"], pr["normal"],
+                pr["offset"], cam["viewmatrix"], cam["campos"], concat_sh=False)
+            rs = U.make_settings(wl.dpr, scv, render_geo=True)
+            res = wl.dpr.GaussianRasterizer(rs)(means3D=pr["xyz"], means2D=z, means2D_abs=z, opacities=opacity,
+                                                shs=pr["f_dc"], shs_rest=pr["f_rest"], scales=scales,
+                                                rotations=rotations, all_map=all_map)
+            return res[0], res[2], res[3], res[5]
+
+        def finish():
+            opt.step(grad_scale=1.0 / Vn, zero_grads=True)
+    else:
+        from oracle import ref_ext
+        from ssim_ref import torch_ssim_map
+        pr = {k: v.clone().requires_grad_(True) for k, v in raw.items()}
+        opt = torch.optim.Adam([{"params": [pr[k]], "lr": lrs[k], "name": k} for k in pr], lr=0.0, eps=1e-15)
+
+        def ssim(a, b):
+            return torch_ssim_map(a, b).mean()
+
+        def compute_photometric_ssim(a, b, size_average=True):
+            m = torch_ssim_map(a, b)
+            return m.mean() if size_average else m
+
+        def render(cam, scv):
+            opacity, scales, rotations, shs, all_map = PR.torch_prologue(
+                pr["xyz"], pr["opacity"], pr["scaling"], pr["rotation"], pr["f_dc"], pr["f_rest"], pr["normal"],
+                pr["offset"], cam["viewmatrix"], cam["campos"])
+            return ref_ext.RefRasterize.apply(pr["xyz"], shs, opacity, scales, rotations, all_map, scv)
+
+        def finish():
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+
+    def step():
+        for cam in wl.views:
+            scv = wl.scene_for(cam)
+            image, normal, depth, warped = render(cam, scv)
+            loss = 0.8 * (image - gt).abs().mean() + 0.2 * (1.0 - ssim(image, gt))
+            w = warped.view(5, 3, wl.H, wl.W)[:4]
+            ph_ssim = 1 - torch.stack([compute_photometric_ssim(gt, w[i], size_average=False).mean(0) for i in range(4)])
+            ph_l1 = (gt[None] - w).abs().mean(1)
+            loss = loss + 0.15 * (0.15 * ph_l1 + 0.85 * ph_ssim).mean()
+            loss = loss + 0.015 * (1 - (normal * nref).sum(0)).mean() + 0.01 * depth.mean()
+            (loss / 1.0).backward()
+        finish()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / (steps * Vn)
+    return {"ms_per_view": ms, "views_per_s": 1000.0 / ms, "views_per_step": Vn, "steps": steps,
+            "stages": "prologue + rasterizer fwd/bwd + L1/SSIM image loss + 4-view photometric L1/SSIM + Adam every "
+                      f"{Vn} views; no colour-aggregation network"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -553,6 +646,15 @@ def main():
                                           "(oracle/_ref) on the same GPU, full workload"}
     elif args.gpus == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args)
+    if args.gpus == 1 and not args.no_train_step:
+        try:
+            if args.impl == "b200":
+                del runner
+            torch.cuda.empty_cache()
+            line["train_step"] = train_step_timing(wl, args.impl)
+        except Exception as ex:  # extra information only: never lose the headline line over it
+            line["train_step"] = {"error": repr(ex)}
+        runner = None
     if args.impl == "b200" and args.gpus == 1:
         try:
             line["source_depth_batch"] = depth_batch_timing(wl)

@@ -83,6 +83,31 @@ def backward(sc, fw, cot, render_geo=True, debug=False):
                 opacities=g_opac, scales=g_scales, rotations=g_rots, cov3D=g_cov3D, all_map=g_all_map)
 
 
+class RefRasterize(torch.autograd.Function):
+    """Minimal autograd wrapper around the reference extension's two entry points, so that bench.py's reference arm can
+    run a whole training step (loss.backward()) through the UNMODIFIED reference rasterizer.  The reference's own
+    Python wrapper (diff_plane_rasterization/__init__.py:21-250) does the same bookkeeping; it is not available on the
+    GPU box (no /root/reference there), and reference sources are never copied into this repo."""
+
+    @staticmethod
+    def forward(ctx, means3D, sh, opacities, scales, rotations, all_map, sc):
+        sc = dict(sc)
+        sc.update(means3D=means3D, shs=sh, opacities=opacities, scales=scales, rotations=rotations, all_map=all_map)
+        fw = forward(sc, render_geo=True)
+        ctx.sc, ctx.fw = sc, fw
+        return fw["color"], fw["normal"], fw["depth"], fw["warped"]
+
+    @staticmethod
+    def backward(ctx, g_color, g_normal, g_depth, g_warped):
+        z = lambda g, ref: torch.zeros_like(ref) if g is None else g.contiguous()
+        fw = ctx.fw
+        cot = dict(color=z(g_color, fw["color"]), normal=z(g_normal, fw["normal"]), depth=z(g_depth, fw["depth"]),
+                   warped=z(g_warped, fw["warped"]))
+        gr = backward(ctx.sc, fw, cot, render_geo=True)
+        return (gr["means3D"], gr["sh"], gr["opacities"].view_as(ctx.sc["opacities"]), gr["scales"], gr["rotations"],
+                gr["all_map"], None)
+
+
 def _al(x, a=128):
     return (x + a - 1) // a * a
 

@@ -16,7 +16,7 @@ timeout 300 python tools/quick_ab.py cfg3_1080p --iters 10 --depth-batch 4 > $OU
 timeout 300 python tools/quick_ab.py cfg3_1080p --iters 10 --depth-only > $OUT/${TAG}_depth_only.log 2>&1
 # launch list of the bench command (shares only: ncu serialises and runs cold)
 IBGS_BENCH_NOCLOCK=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-  --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline \
+  --log-file $OUT/${TAG}_launches_bench.csv python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-train-step \
   > $OUT/${TAG}_launches_bench.log 2>&1
 # full capture of the two tile renderers + sort + preprocess backward, one launch each, warm
 timeout 600 ncu --set full --clock-control none --import-source on \

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
         // The reference evaluates exp() here and __expf in the forward (backward.cu:648, forward.cu:424).  The fast
         // one is used in both passes: same accept/reject decisions as our (and the reference's) forward, 2 ulp
         // from exp() -- five orders of magnitude below the 1e-3 gradient gate.
-        const float G = __expf(power);
+        const float G = exp_power(power);
         const float alpha = min(0.99f, g1.y * G);
         const bool active = inside && !(contributor >= last_contributor) && !(power > 0.0f) &&
                             !(alpha < 1.0f / 255.0f);

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
         // con_o = (g0.z, g0.w, g1.x, g1.y); forward.cu:421-427
         const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
         if (power > 0.0f) continue;
-        const float alpha = min(0.99f, g1.y * __expf(power));
+        const float alpha = min(0.99f, g1.y * exp_power(power));
         if (alpha < 1.0f / 255.0f) continue;
         const float test_T = T * (1.0f - alpha);
         if (test_T < 0.0001f) { done = true; continue; }

@@ -271,7 +271,7 @@ __device__ __forceinline__ void median_pair_backward(const BwdArgs& a, const flo
     }
   }
   dL_dalpha *= Te;
-  dL_dalpha += (-T_final * __fdividef(1.f, 1.f - alpha)) * bg_dot_dpixel;
+  dL_dalpha += (-T_final * rcp_approx(1.f - alpha)) * bg_dot_dpixel;
   // same UNSCALED slot convention as the pair loop (see there)
   const float dL_dG = g1.y * dL_dalpha;
   const float gdx = G * d.x;
@@ -303,14 +303,19 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // ---------------------------------------------------------------------------------------------------------
 // kernel A: the pair loop
 // ---------------------------------------------------------------------------------------------------------
-template <bool GEO, int MAXE, int NSRC>
-__global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const BwdArgs a) {
+// PPL = pixels per lane.  PPL == 1: eight warps per tile, warp = 8x4 pixels.  PPL == 2: four warps per tile, warp =
+// 8x8 pixels, lane = the two pixels (x, y) and (x, y + 4): the two pixels of a lane contribute to the SAME Gaussian, so
+// their 15 terms are added in registers and ONE shared-memory reduction serves 64 pixels instead of 32; the two
+// per-pixel dependency chains also interleave in the instruction stream.
+template <bool GEO, int MAXE, int NSRC, int PPL>
+__global__ void __launch_bounds__(256 / PPL, PPL == 1 ? 3 : 4) render_backward_pairs_kernel(const BwdArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
-  // dynamic shared memory (BWD_SMEM_BYTES): record double buffers | reduction tiles | source-view matrices
+  constexpr int NW = 8 / PPL;  // warps per CTA (= per tile)
+  // dynamic shared memory: record double buffers | reduction tiles | source-view matrices
   extern __shared__ float4 s_dyn[];
   float4(*s_rec)[2][4][32] = reinterpret_cast<float4(*)[2][4][32]>(s_dyn);
-  float* s_red_all = reinterpret_cast<float*>(s_dyn + 8 * 2 * 4 * 32);
-  float* s_ref_to_src = s_red_all + 8 * RED_WARP_FLOATS;
+  float* s_red_all = reinterpret_cast<float*>(s_dyn + NW * 2 * 4 * 32);
+  float* s_ref_to_src = s_red_all + NW * RED_WARP_FLOATS;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -318,11 +323,20 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
   const int W = a.W, H = a.H;
   const int HW = H * W;
   const int sub_x0 = blockIdx.x * TILE + (warp & 1) * 8;
-  const int sub_y0 = blockIdx.y * TILE + (warp >> 1) * 4;
-  const uint2 pix = {(unsigned)(sub_x0 + (lane & 7)), (unsigned)(sub_y0 + (lane >> 3))};
-  const uint32_t pix_id = W * pix.y + pix.x;
-  const float2 pixf = {(float)pix.x, (float)pix.y};
-  const bool inside = pix.x < (unsigned)W && pix.y < (unsigned)H;
+  const int sub_y0 = blockIdx.y * TILE + (warp >> 1) * 4 * PPL;
+  const unsigned px = (unsigned)(sub_x0 + (lane & 7));
+  const float pixfx = (float)px;
+  unsigned py[PPL];
+  uint32_t pix_id[PPL];
+  float pixfy[PPL];
+  bool inside[PPL];
+#pragma unroll
+  for (int q = 0; q < PPL; q++) {
+    py[q] = (unsigned)(sub_y0 + (lane >> 3) + 4 * q);
+    pix_id[q] = W * py[q] + px;
+    pixfy[q] = (float)py[q];
+    inside[q] = px < (unsigned)W && py[q] < (unsigned)H;
+  }
 
   const uint2 range = a.ranges[blockIdx.y * gridDim.x + blockIdx.x];
   const int total = (int)(range.y - range.x);
@@ -332,50 +346,55 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
     __syncthreads();  // the only CTA barrier
   }
 
-  const float T_final = inside ? a.final_T[pix_id] : 0;
-  float T = T_final;
-  const uint32_t last_contributor = inside ? a.n_contrib[pix_id] : 0;
-  // backward.cu:693 compares the unsigned contributor with (int) low-1 / high-1: same unsigned wrap here
-  const uint32_t median_lo = (GEO && inside) ? (uint32_t)((int)a.low[pix_id] - 1) : 1u;
-  const uint32_t median_hi = (GEO && inside) ? (uint32_t)((int)a.high[pix_id] - 1) : 0u;
-  const uint32_t warp_max_contrib = __reduce_max_sync(FULL, last_contributor);
-
-  float accum_rec[3] = {0.f, 0.f, 0.f};
-  float accum_nrm[3] = {0.f, 0.f, 0.f};
-  float dL_dpixel[3] = {0.f, 0.f, 0.f};
-  float dL_dnormal[3] = {0.f, 0.f, 0.f};
-  if (inside) {
+  float T[PPL], bgT[PPL];
+  uint32_t last_contributor[PPL], median_lo[PPL], median_hi[PPL];
+  float accum_rec[PPL][3], accum_nrm[PPL][3], dL_dpixel[PPL][3], dL_dnormal[PPL][3];
+  float rayy[PPL];
+  int ent_n[PPL];
+  uint32_t lane_max_contrib = 0;
 #pragma unroll
-    for (int i = 0; i < 3; i++) dL_dpixel[i] = a.dL_dpixels[i * HW + pix_id];
-    if (GEO) {
+  for (int q = 0; q < PPL; q++) {
+    const float T_final = inside[q] ? a.final_T[pix_id[q]] : 0;
+    T[q] = T_final;
+    last_contributor[q] = inside[q] ? a.n_contrib[pix_id[q]] : 0;
+    lane_max_contrib = max(lane_max_contrib, last_contributor[q]);
+    // backward.cu:693 compares the unsigned contributor with (int) low-1 / high-1: same unsigned wrap here
+    median_lo[q] = (GEO && inside[q]) ? (uint32_t)((int)a.low[pix_id[q]] - 1) : 1u;
+    median_hi[q] = (GEO && inside[q]) ? (uint32_t)((int)a.high[pix_id[q]] - 1) : 0u;
 #pragma unroll
-      for (int i = 0; i < 3; i++) dL_dnormal[i] = a.dL_dnormals[i * HW + pix_id];
+    for (int i = 0; i < 3; i++) {
+      accum_rec[q][i] = 0.f;
+      accum_nrm[q][i] = 0.f;
+      dL_dpixel[q][i] = inside[q] ? a.dL_dpixels[i * HW + pix_id[q]] : 0.f;
+      dL_dnormal[q][i] = (GEO && inside[q]) ? a.dL_dnormals[i * HW + pix_id[q]] : 0.f;
     }
-  }
-  float bg_dot_dpixel = 0;  // backward.cu:779-781
+    float bg_dot_dpixel = 0;  // backward.cu:779-781
 #pragma unroll
-  for (int i = 0; i < 3; i++) bg_dot_dpixel += a.bg[i] * dL_dpixel[i];
-  const float bgT = -T_final * bg_dot_dpixel;
-  if (GEO && inside) {
-    // phase B (after the pair loop) reads these per-pixel values with dependent loads: pull them into L2 now
-    prefetch_l2(a.sum_w + pix_id);
-    prefetch_l2(a.depth_pixels + pix_id);
-    prefetch_l2(a.dL_ddepths + pix_id);
+    for (int i = 0; i < 3; i++) bg_dot_dpixel += a.bg[i] * dL_dpixel[q][i];
+    bgT[q] = -T_final * bg_dot_dpixel;
+    if (GEO && inside[q]) {
+      // phase B (after the pair loop) reads these per-pixel values with dependent loads: pull them into L2 now
+      prefetch_l2(a.sum_w + pix_id[q]);
+      prefetch_l2(a.depth_pixels + pix_id[q]);
+      prefetch_l2(a.dL_ddepths + pix_id[q]);
 #pragma unroll
-    for (int mm = 0; mm < NSRC; mm++) {
-      prefetch_l2(a.valid_idx + mm * HW + pix_id);
-      prefetch_l2(a.valid_w + mm * HW + pix_id);
+      for (int mm = 0; mm < NSRC; mm++) {
+        prefetch_l2(a.valid_idx + mm * HW + pix_id[q]);
+        prefetch_l2(a.valid_w + mm * HW + pix_id[q]);
 #pragma unroll
-      for (int n_i = 0; n_i < 3; n_i++) {
-        prefetch_l2(a.dL_dwarped + (mm * 3 + n_i) * HW + pix_id);
-        prefetch_l2(a.warped_pixels + (mm * 3 + n_i) * HW + pix_id);
+        for (int n_i = 0; n_i < 3; n_i++) {
+          prefetch_l2(a.dL_dwarped + (mm * 3 + n_i) * HW + pix_id[q]);
+          prefetch_l2(a.warped_pixels + (mm * 3 + n_i) * HW + pix_id[q]);
+        }
       }
     }
+    // the pair loop only needs the SIGN of the plane depth (recorded pairs are re-evaluated exactly, in the
+    // reference's double/float mix, by phase B)
+    rayy[q] = (pixfy[q] - 0.5f * (float)H) / a.fy;
+    ent_n[q] = 0;
   }
-  // the pair loop only needs the SIGN of the plane depth (recorded pairs are re-evaluated exactly, in the
-  // reference's double/float mix, by render_backward_median_kernel)
-  const float2 ray = {(pixf.x - 0.5f * (float)W) / a.fx, (pixf.y - 0.5f * (float)H) / a.fy};
-  int ent_n = 0;
+  const float rayx = (pixfx - 0.5f * (float)W) / a.fx;
+  const uint32_t warp_max_contrib = __reduce_max_sync(FULL, lane_max_contrib);
 
   float* arena_f = reinterpret_cast<float*>(a.arena);
   float4(*wrec)[4][32] = s_rec[warp];
@@ -391,7 +410,7 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
 
   if (c_begin < nchunks) {
     const float wx0 = (float)sub_x0, wx1 = (float)(sub_x0 + 7);
-    const float wy0 = (float)sub_y0, wy1 = (float)(sub_y0 + 3);
+    const float wy0 = (float)sub_y0, wy1 = (float)(sub_y0 + 4 * PPL - 1);
     uint32_t id_next = 0u;  // id of this lane's Gaussian in the step being fetched
     {
       const int p = (c_begin << 5) + lane;
@@ -444,89 +463,101 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
         const uint32_t contributor = (uint32_t)(total - 1 - c0 - b);  // backward.cu:636
         const float4 g0 = wrec[buf][0][b];
         const float4 g1 = wrec[buf][1][b];
-        const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
-        const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
-        // The reference evaluates exp() here and __expf in the forward (backward.cu:648, forward.cu:424).  The fast
-        // one is used in both passes: same accept/reject decisions as our (and the reference's) forward, 2 ulp
-        // from exp() -- five orders of magnitude below the 1e-3 gradient gate.
-        const float G = exp_power(power);
-        const float alpha = min(0.99f, g1.y * G);
-        const bool active = inside && !(contributor >= last_contributor) && !(power > 0.0f) &&
-                            !(alpha < 1.0f / 255.0f);
-        if (!__any_sync(FULL, active)) continue;
+        const float dx = g0.x - pixfx;
+        float dy[PPL], G[PPL], alpha[PPL];
+        bool active[PPL];
+        bool any_active = false;
+#pragma unroll
+        for (int q = 0; q < PPL; q++) {
+          dy[q] = g0.y - pixfy[q];
+          const float power = -0.5f * (g0.z * dx * dx + g1.x * dy[q] * dy[q]) - g0.w * dx * dy[q];
+          // The reference evaluates exp() here and __expf in the forward (backward.cu:648, forward.cu:424).  The fast
+          // one is used in both passes: same accept/reject decisions as our (and the reference's) forward, 2 ulp
+          // from exp() -- five orders of magnitude below the 1e-3 gradient gate.
+          G[q] = exp_power(power);
+          alpha[q] = min(0.99f, g1.y * G[q]);
+          active[q] = inside[q] && !(contributor >= last_contributor[q]) && !(power > 0.0f) &&
+                      !(alpha[q] < 1.0f / 255.0f);
+          any_active = any_active || active[q];
+        }
+        if (!__any_sync(FULL, any_active)) continue;
         const uint32_t gid = __shfl_sync(FULL, id_cur, b);
 
         float v[16];
 #pragma unroll
         for (int k = 0; k < 16; k++) v[k] = 0.0f;
 
-        if (active) {
-          // 1/(1-alpha) once, approximate reciprocal (2 ulp): gradients are compared at 1e-3 relative L2 and
-          // summed in a different order than the reference anyway
-          const float one_m_alpha = 1.f - alpha;
-          const float rinv = __fdividef(1.f, one_m_alpha);
-          T = T * rinv;
-          const float dchannel_dcolor = alpha * T;
-          float dL_dalpha = 0.0f;
-          const float4 g2 = wrec[buf][2][b];
-          const float col[3] = {g2.x, g2.y, g2.z};
-          // accum_rec holds the blend of everything BEHIND this pair; the reference folds the previous pair in
-          // at the top of the next iteration (last_alpha / last_color, backward.cu:661-668) -- same values,
-          // folded here at the bottom of the current one instead, which frees seven registers
-          // (alpha*c + (1-alpha)*accum is evaluated as accum + alpha*(c - accum): the difference is needed anyway)
 #pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            const float diff = col[ch] - accum_rec[ch];
-            const float dL_dchannel = dL_dpixel[ch];
-            dL_dalpha += diff * dL_dchannel;
-            v[8 + ch] = dchannel_dcolor * dL_dchannel;
-            accum_rec[ch] += alpha * diff;
-          }
-          bool deferred = false;
-          if (GEO) {
-            const float4 g3 = wrec[buf][3][b];
-            const float nrm[3] = {g3.x, g3.y, g3.z};
+        for (int q = 0; q < PPL; q++) {
+          if (active[q]) {
+            // 1/(1-alpha) once, approximate reciprocal (2 ulp): gradients are compared at 1e-3 relative L2 and
+            // summed in a different order than the reference anyway
+            const float one_m_alpha = 1.f - alpha[q];
+            const float rinv = rcp_approx(one_m_alpha);  // one_m_alpha in [0.01, 1]: no denormal rescue path needed
+            T[q] = T[q] * rinv;
+            const float dchannel_dcolor = alpha[q] * T[q];
+            float dL_dalpha = 0.0f;
+            const float4 g2 = wrec[buf][2][b];
+            const float col[3] = {g2.x, g2.y, g2.z};
+            // accum_rec holds the blend of everything BEHIND this pair; the reference folds the previous pair in
+            // at the top of the next iteration (last_alpha / last_color, backward.cu:661-668) -- same values,
+            // folded here at the bottom of the current one instead, which frees seven registers
+            // (alpha*c + (1-alpha)*accum is evaluated as accum + alpha*(c - accum): the difference is needed anyway)
 #pragma unroll
             for (int ch = 0; ch < 3; ch++) {
-              const float diff = nrm[ch] - accum_nrm[ch];
-              const float dL_dchannel = dL_dnormal[ch];
+              const float diff = col[ch] - accum_rec[q][ch];
+              const float dL_dchannel = dL_dpixel[q][ch];
               dL_dalpha += diff * dL_dchannel;
-              v[12 + ch] = dchannel_dcolor * dL_dchannel;
-              accum_nrm[ch] += alpha * diff;
+              v[8 + ch] += dchannel_dcolor * dL_dchannel;
+              accum_rec[q][ch] += alpha[q] * diff;
             }
-            // median buffer, backward.cu:693-701: a pair in range with a valid plane depth is only RECORDED
-            // here (Gaussian id, T, colour+normal part of dL/dalpha); render_backward_median_kernel does the rest
-            if (contributor >= median_lo && contributor <= median_hi) {
-              // intersected_depth = -d / (n.ray + 1e-8) > 0  <=>  d and the denominator have opposite signs
-              const float z_den = g3.x * ray.x + g3.y * ray.y + g3.z + 1.0e-8f;
-              const bool z_pos = (g2.w > 0.0f && z_den < 0.0f) || (g2.w < 0.0f && z_den > 0.0f);
-              if (z_pos && ent_n < MAXE) {
-                float* e = a.ent + ((size_t)ent_n * HW + pix_id);
-                e[0] = __uint_as_float(gid);
-                e[a.ent_stride] = T;
-                e[2 * a.ent_stride] = dL_dalpha;
-                ent_n++;
-                deferred = true;
+            bool deferred = false;
+            if (GEO) {
+              const float4 g3 = wrec[buf][3][b];
+              const float nrm[3] = {g3.x, g3.y, g3.z};
+#pragma unroll
+              for (int ch = 0; ch < 3; ch++) {
+                const float diff = nrm[ch] - accum_nrm[q][ch];
+                const float dL_dchannel = dL_dnormal[q][ch];
+                dL_dalpha += diff * dL_dchannel;
+                v[12 + ch] += dchannel_dcolor * dL_dchannel;
+                accum_nrm[q][ch] += alpha[q] * diff;
+              }
+              // median buffer, backward.cu:693-701: a pair in range with a valid plane depth is only RECORDED
+              // here (Gaussian id, T, colour+normal part of dL/dalpha); phase B does the rest
+              if (contributor >= median_lo[q] && contributor <= median_hi[q]) {
+                // intersected_depth = -d / (n.ray + 1e-8) > 0  <=>  d and the denominator have opposite signs
+                const float z_den = g3.x * rayx + g3.y * rayy[q] + g3.z + 1.0e-8f;
+                const bool z_pos = (g2.w > 0.0f && z_den < 0.0f) || (g2.w < 0.0f && z_den > 0.0f);
+                if (z_pos && ent_n[q] < MAXE) {
+                  float* e = a.ent + ((size_t)ent_n[q] * HW + pix_id[q]);
+                  e[0] = __uint_as_float(gid);
+                  e[a.ent_stride] = T[q];
+                  e[2 * a.ent_stride] = dL_dalpha;
+                  ent_n[q]++;
+                  deferred = true;
+                }
               }
             }
-          }
-          if (!deferred) {
-            dL_dalpha *= T;
-            dL_dalpha += bgT * rinv;
-            const float dL_dG = g1.y * dL_dalpha;
-            const float gdx = G * d.x;
-            const float gdy = G * d.y;
-            const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
-            const float dG_ddely = -gdy * g1.x - gdx * g0.w;
-            v[0] = dL_dG * dG_ddelx;
-            v[1] = dL_dG * dG_ddely;
-            v[2] = fabs(v[0]);
-            v[3] = fabs(v[1]);
-            const float hx = dL_dG * gdx, hy = dL_dG * gdy;
-            v[4] = hx * d.x;
-            v[5] = hx * d.y;
-            v[6] = hy * d.y;
-            v[7] = G * dL_dalpha;
+            if (!deferred) {
+              dL_dalpha *= T[q];
+              dL_dalpha += bgT[q] * rinv;
+              const float dL_dG = g1.y * dL_dalpha;
+              const float gdx = G[q] * dx;
+              const float gdy = G[q] * dy[q];
+              const float dG_ddelx = -gdx * g0.z - gdy * g0.w;
+              const float dG_ddely = -gdy * g1.x - gdx * g0.w;
+              const float t0 = dL_dG * dG_ddelx, t1 = dL_dG * dG_ddely;
+              v[0] += t0;
+              v[1] += t1;
+              v[2] += fabs(t0);
+              v[3] += fabs(t1);
+              const float hx = dL_dG * gdx, hy = dL_dG * gdy;
+              v[4] += hx * dx;
+              v[5] += hx * dy[q];
+              v[6] += hy * dy[q];
+              v[7] += G[q] * dL_dalpha;
+            }
           }
         }
 
@@ -539,18 +570,43 @@ __global__ void __launch_bounds__(256, 3) render_backward_pairs_kernel(const Bwd
     }
     cp_async_wait<0>();
   }
-  // ---- phase B: this pixel's recorded median-buffer pairs (its own writes above: no fence needed) ----
-  if (GEO && inside) {
+  // ---- phase B: this lane's recorded median-buffer pairs (its own writes above: no fence needed) ----
+  if (GEO) {
+#pragma unroll
+    for (int q = 0; q < PPL; q++) {
+      if (!inside[q]) continue;
 #pragma unroll 1
-    for (int e = 0; e < ent_n; e++) median_pair_backward<NSRC>(a, s_ref_to_src, pix, pix_id, e);
+      for (int e = 0; e < ent_n[q]; e++)
+        median_pair_backward<NSRC>(a, s_ref_to_src, make_uint2(px, py[q]), pix_id[q], e);
+    }
   }
 }
 
-constexpr int BWD_SMEM_BYTES = 8 * 2 * 4 * 32 * 16 + 8 * RED_WARP_FLOATS * 4 + MAX_SRC * 16 * 4;
+// IBGS_BWD_PPL forces one variant (kernel experiments); by default launch_render_backward picks per view
+#ifndef IBGS_BWD_PPL
+#define IBGS_BWD_PPL 0
+#endif
+constexpr int bwd_smem_bytes(int ppl) {
+  return (8 / ppl) * (2 * 4 * 32 * 16 + RED_WARP_FLOATS * 4) + MAX_SRC * 16 * 4;
+}
+// average tile-list length from which the 2-pixels-per-lane variant wins (measured: 126 instances per tile -> 8 %
+// slower, 1894 per tile -> 9 % faster; short lists are dominated by the per-pixel set-up and phase B, which the
+// 4-warp CTAs serialise)
+constexpr long long BWD_DENSE_LIST = 512;
+int g_bwd_variant = IBGS_BWD_PPL;   // 0 = choose per view, 1 / 2 = forced (ibgs_set_backward_variant)
 
 inline int max_entries(int buffer_length) { return buffer_length <= 4 ? 5 : 9; }
 
 }  // namespace
+
+extern "C" int ibgs_set_backward_variant(int pixels_per_lane) {
+  if (pixels_per_lane < 0 || pixels_per_lane > 2) {
+    ibgs_set_error("pixels_per_lane must be 0 (choose per view), 1 or 2, got %d", pixels_per_lane);
+    return IBGS_EINVAL;
+  }
+  g_bwd_variant = pixels_per_lane;
+  return IBGS_OK;
+}
 
 size_t render_backward_scratch_bytes(size_t N, int buffer_length, int render_geo) {
   if (!render_geo) return 0;
@@ -599,12 +655,18 @@ int launch_render_backward(const IbgsBackwardArgs& f, const GeomState& g, const 
   }
   ProfScope prof(PROF_RENDER_BWD, s);
   // > 48 KB of shared memory needs the opt-in attribute (per device; cheap enough to set per launch)
+#define LAUNCH_PAIRS_PPL(PPL, ...)                                                                             \
+  do {                                                                                                         \
+    CUDA_TRY(cudaFuncSetAttribute(render_backward_pairs_kernel<__VA_ARGS__, PPL>,                              \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem_bytes(PPL)));          \
+    render_backward_pairs_kernel<__VA_ARGS__, PPL><<<grid, 256 / PPL, bwd_smem_bytes(PPL), s>>>(a);            \
+  } while (0)
 #define LAUNCH_PAIRS(...)                                                                                      \
   do {                                                                                                         \
-    CUDA_TRY(cudaFuncSetAttribute(render_backward_pairs_kernel<__VA_ARGS__>,                                   \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM_BYTES));               \
-    render_backward_pairs_kernel<__VA_ARGS__><<<grid, 256, BWD_SMEM_BYTES, s>>>(a);                            \
+    if (two_per_lane) LAUNCH_PAIRS_PPL(2, __VA_ARGS__); else LAUNCH_PAIRS_PPL(1, __VA_ARGS__);                 \
   } while (0)
+  const long long tiles = (long long)grid.x * grid.y;
+  const bool two_per_lane = g_bwd_variant ? (g_bwd_variant == 2) : ((long long)f.R > BWD_DENSE_LIST * tiles);
   if (f.view.render_geo) {
     const bool few = f.view.nb_src_images <= 4;  // the callers' default is 4 source views (arguments/__init__.py:127)
     if (f.view.buffer_length <= 4) {
@@ -615,6 +677,7 @@ int launch_render_backward(const IbgsBackwardArgs& f, const GeomState& g, const 
   } else {
     LAUNCH_PAIRS(false, 1, 1);
   }
+#undef LAUNCH_PAIRS_PPL
 #undef LAUNCH_PAIRS
   KERNEL_CHECK(f.view.debug, s);
   return IBGS_OK;

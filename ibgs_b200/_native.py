@@ -109,7 +109,7 @@ EXPORTS = [
     "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
     "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
     "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
-    "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward", "ibgs_adam_step", "ibgs_set_backward_variant",
+    "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward", "ibgs_adam_step", "ibgs_set_backward_variant", "ibgs_set_forward_variant",
 ]
 
 
@@ -157,8 +157,9 @@ def _load():
     for fn in (lib.ibgs_ssim_forward, lib.ibgs_ssim_backward):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(IbgsSsimArgs), C.c_void_p]
-    lib.ibgs_set_backward_variant.restype = C.c_int
-    lib.ibgs_set_backward_variant.argtypes = [C.c_int]
+    for fn in (lib.ibgs_set_backward_variant, lib.ibgs_set_forward_variant):
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int]
     lib.ibgs_adam_step.restype = C.c_int
     lib.ibgs_adam_step.argtypes = [C.POINTER(IbgsAdamArgs), C.c_void_p]
     lib.ibgs_forward_depth_batch.restype = C.c_int64

@@ -248,7 +248,7 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
   rc = run_binning(*a, g, ord, im, scratch_base, scratch_bytes, b, R, grid, s);
   if (rc != IBGS_OK) return rc;
 
-  rc = launch_render_forward(*a, g, im, b, tex, focal_x, focal_y, grid, s);
+  rc = launch_render_forward(*a, g, im, b, tex, focal_x, focal_y, grid, R, s);
   if (rc != IBGS_OK) return rc;
   return R;
 }
@@ -348,7 +348,7 @@ extern "C" int64_t ibgs_forward_depth_batch(IbgsDepthBatchArgs* a, void* stream_
   carve_binning(b, base2, (size_t)R);
   rc = run_binning_items((int)items, radii, a->debug, V, g, ord, ranges, base2 + bin_bytes, scratch_bytes, b, R, grid, s);
   if (rc != IBGS_OK) return rc;
-  rc = launch_render_depth_batch(*a, g, ranges, b, focal_x, focal_y, grid, s);
+  rc = launch_render_depth_batch(*a, g, ranges, b, focal_x, focal_y, grid, R, s);
   if (rc != IBGS_OK) return rc;
   return R;
 }

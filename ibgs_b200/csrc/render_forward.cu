@@ -69,197 +69,18 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// Per-pixel epilogue (forward.cu:496-664): final transmittance / contributor count, colour + background, depth-only
+// quotient, and in render_geo mode the multi-view warp block.  One call per pixel of the lane.
 template <int MODE, int BL>
-__global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a) {
-  constexpr int BEFORE = (BL + 1) / 2;  // forward.cu:384
-  constexpr int BELOW = BL - BEFORE;    // forward.cu:385
-  constexpr unsigned FULL = 0xffffffffu;
-
-  // per-warp double buffer: [warp][buf][quad][lane]
-  __shared__ float4 s_rec[8][2][4][32];
-  __shared__ float s_ref_to_src[MAX_SRC * 16];
-  __shared__ float s_src_cam_pos[MAX_SRC * 3];
-
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const int warp = tid >> 5;
+__device__ __forceinline__ void render_forward_epilogue(const FwdArgs& a, const float* s_ref_to_src,
+                                                        const float* s_src_cam_pos, uint32_t pix_id, float pixfx,
+                                                        float pixfy, int HW, float T, uint32_t last_contributor,
+                                                        const float (&C)[3], const float (&normal_accum)[3],
+                                                        const float (&zb)[BL], const float (&wb)[BL],
+                                                        const float (&db)[BL], const uint32_t (&cb)[BL],
+                                                        float total_buffer_weight, float weighted_depth_sum) {
   const int W = a.W, H = a.H;
-  // warp w -> 8x4 sub-tile (2 across, 4 down); lane -> pixel inside it
-  const int sub_x0 = blockIdx.x * TILE + (warp & 1) * 8;
-  const int sub_y0 = blockIdx.y * TILE + (warp >> 1) * 4;
-  const uint2 pix = {(unsigned)(sub_x0 + (lane & 7)), (unsigned)(sub_y0 + (lane >> 3))};
-  // blockIdx.z = view of a batched depth-only launch (0 otherwise): its tile ranges and output plane follow view z-1's
-  const uint32_t pix_id = (MODE == MODE_DEPTH ? blockIdx.z * (uint32_t)(W * H) : 0u) + W * pix.y + pix.x;
-  const float2 pixf = {(float)pix.x, (float)pix.y};
-  const float2 ray = {(pixf.x - a.cx) / a.focal_x, (pixf.y - a.cy) / a.focal_y};  // forward.cu:352
-  const bool inside = pix.x < (unsigned)W && pix.y < (unsigned)H;
-  bool done = !inside;
-
-  // sub-tile bounds for the cull test
-  const float wx0 = (float)sub_x0, wx1 = (float)(sub_x0 + 7);
-  const float wy0 = (float)sub_y0, wy1 = (float)(sub_y0 + 3);
-
-  const uint2 range = a.ranges[((MODE == MODE_DEPTH ? blockIdx.z * gridDim.y : 0u) + blockIdx.y) * gridDim.x + blockIdx.x];
-  const int total = (int)(range.y - range.x);
-
-  if (MODE == MODE_GEO) {
-    if (tid < a.nb_src * 16) s_ref_to_src[tid] = a.ref_to_src_list[tid];
-    if (tid < a.nb_src * 3) s_src_cam_pos[tid] = a.src_cam_pos[tid];
-    __syncthreads();  // the only CTA barrier: epilogue constants
-  }
-
   const float epsilon = 1.0e-8f;
-  float T = 1.0f;
-  uint32_t last_contributor = 0;
-  float C[3] = {0.f, 0.f, 0.f};
-  float normal_accum[3] = {0.f, 0.f, 0.f};
-  float zb[BL], wb[BL], db[BL];   // GEO: zb = depth denominator, db = plane distance; DEPTH: zb = depth
-  uint32_t cb[BL];
-#pragma unroll
-  for (int k = 0; k < BL; k++) { zb[k] = 0.f; wb[k] = 0.f; db[k] = 0.f; cb[k] = 0u; }
-  int before_ptr = 0;
-  int below_count = 0;
-  float total_buffer_weight = 0.0f;
-  float weighted_depth_sum = 0.0f;
-  // depth-only with BELOW==0 (BL==1): the reference `break`s out of the current 256-instance batch only
-  // (forward.cu:484-488) and resumes with the next one
-  bool brk = false;
-
-  const uint32_t* plist = a.point_list + range.x;
-  const int nchunks = (total + 31) >> 5;
-  float4(*wrec)[4][32] = s_rec[warp];
-
-  // software pipeline: ids two steps ahead (register), records one step ahead (cp.async)
-  uint32_t id_issue = (lane < total) ? plist[lane] : 0u;
-  if (nchunks > 0 && !__all_sync(FULL, done)) {
-    if (lane < total) {
-      const float4* r = a.rec + 4 * (size_t)id_issue;
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (k < 3 || MODE != MODE_COLOR) cp_async16(&wrec[0][k][lane], r + k);
-    }
-    cp_async_commit();
-    id_issue = (32 + lane < total) ? plist[32 + lane] : 0u;
-
-    for (int c = 0; c < nchunks; c++) {
-      const int buf = c & 1;
-      const int c0 = c << 5;
-      if (c + 1 < nchunks) {
-        if (c0 + 32 + lane < total) {
-          const float4* r = a.rec + 4 * (size_t)id_issue;
-#pragma unroll
-          for (int k = 0; k < 4; k++)
-            if (k < 3 || MODE != MODE_COLOR) cp_async16(&wrec[buf ^ 1][k][lane], r + k);
-        }
-        id_issue = (c0 + 64 + lane < total) ? plist[c0 + 64 + lane] : 0u;
-      }
-      cp_async_commit();
-      cp_async_wait<1>();   // everything but the newest group has landed -> step c is in shared memory
-      __syncwarp();
-      if ((c0 & (TILE_PIX - 1)) == 0) brk = false;  // new 256-instance batch of the reference
-
-      const int j = c0 + lane;
-      bool keep = false;
-      if (j < total) {
-        const float4 q0 = wrec[buf][0][lane];
-        const float4 q1 = wrec[buf][1][lane];
-        keep = subtile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, wx0, wx1, wy0, wy1);
-      }
-      unsigned m = __ballot_sync(FULL, keep);
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        if (done || brk) continue;
-        const uint32_t contributor = (uint32_t)(c0 + b + 1);  // forward.cu:417
-        const float4 g0 = wrec[buf][0][b];
-        const float4 g1 = wrec[buf][1][b];
-        const float2 d = {g0.x - pixf.x, g0.y - pixf.y};
-        // con_o = (g0.z, g0.w, g1.x, g1.y); forward.cu:421-427
-        const float power = -0.5f * (g0.z * d.x * d.x + g1.x * d.y * d.y) - g0.w * d.x * d.y;
-        if (power > 0.0f) continue;
-        const float alpha = min(0.99f, g1.y * exp_power(power));
-        if (alpha < 1.0f / 255.0f) continue;
-        const float test_T = T * (1.0f - alpha);
-        if (test_T < 0.0001f) { done = true; continue; }
-        const float aT = alpha * T;
-
-        const float4 g2 = wrec[buf][2][b];
-        if (MODE != MODE_DEPTH) {
-          C[0] += g2.x * aT;
-          C[1] += g2.y * aT;
-          C[2] += g2.z * aT;
-        }
-        if (MODE != MODE_COLOR) {
-          const float4 g3 = wrec[buf][3][b];
-          // forward.cu:439-442: intersected_depth = -d / (n.ray + eps)
-          const float z_den = g3.x * ray.x + g3.y * ray.y + g3.z + epsilon;
-          if (MODE == MODE_GEO) {
-            normal_accum[0] += g3.x * aT;
-            normal_accum[1] += g3.y * aT;
-            normal_accum[2] += g3.z * aT;
-            // The ring only ever needs the depths of the entries it still holds at the end, so the IEEE
-            // division is postponed to the epilogue: the ring stores the denominator (the numerator -d is
-            // re-read there).  "depth > 0" is decided from the operand signs: -d/den > 0 <=> d and den are
-            // non-zero with opposite signs (den = 0 gives +-inf of the wrong sign or NaN, NaN compares false;
-            // the quotient cannot underflow to 0 for finite plane parameters and a ray inside the frustum).
-            const bool need = (T > 0.5f) || (below_count < BELOW);
-            const bool z_pos = (g2.w > 0.0f && z_den < 0.0f) || (g2.w < 0.0f && z_den > 0.0f);
-            if (need && z_pos) {
-              if (T > 0.5f) {
-#pragma unroll
-                for (int k = 0; k < BEFORE; k++)
-                  if (before_ptr == k) { zb[k] = z_den; db[k] = g2.w; wb[k] = aT; cb[k] = contributor; }
-                before_ptr = (before_ptr + 1) % BEFORE;
-              } else {
-#pragma unroll
-                for (int k = 0; k < BELOW; k++)
-                  if (below_count == k) {
-                    zb[BEFORE + k] = z_den; db[BEFORE + k] = g2.w; wb[BEFORE + k] = aT; cb[BEFORE + k] = contributor;
-                  }
-                below_count++;
-              }
-            }
-          } else {  // MODE_DEPTH, forward.cu:466-489
-            const float intersected_depth = -g2.w / z_den;
-            if (intersected_depth > 0.0f) {
-              if (T > 0.5f) {
-                float old_w = 0.f, old_z = 0.f;
-#pragma unroll
-                for (int k = 0; k < BEFORE; k++)
-                  if (before_ptr == k) {
-                    old_w = wb[k]; old_z = zb[k];
-                    zb[k] = intersected_depth; wb[k] = aT;
-                  }
-                total_buffer_weight -= old_w;
-                weighted_depth_sum -= old_w * old_z;
-                before_ptr = (before_ptr + 1) % BEFORE;
-                total_buffer_weight += aT;
-                weighted_depth_sum += aT * intersected_depth;
-              } else if (below_count < BELOW) {
-                below_count++;
-                total_buffer_weight += aT;
-                weighted_depth_sum += aT * intersected_depth;
-              }
-              if (below_count == BELOW) {
-                // BELOW>0: T<=0.5 from here on, the sums are final -> the pixel is finished.
-                // BELOW==0: reference semantics = leave this batch, resume at the next.
-                if (BELOW > 0) done = true; else brk = true;
-              }
-            }
-          }
-        }
-        T = test_T;
-        last_contributor = contributor;
-      }
-      if (__all_sync(FULL, done)) break;   // warp-level early termination
-      __syncwarp();  // every lane is done reading buf before the step after next overwrites it (a vote is not a
-                     // memory-ordering barrier; compute-sanitizer racecheck flags the re-use without this)
-    }
-    cp_async_wait<0>();
-  }
-
-  if (!inside) return;
-  const int HW = H * W;
   if (MODE != MODE_DEPTH || a.final_T != nullptr) {  // the batched depth launch keeps no image state
     a.final_T[pix_id] = T;
     a.n_contrib[pix_id] = last_contributor;
@@ -276,8 +97,8 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
     // forward.cu:512-663
     const float inv_focal_x = 1.0f / a.focal_x;
     const float inv_focal_y = 1.0f / a.focal_y;
-    const float pix_diff_x = pixf.x - a.cx;
-    const float pix_diff_y = pixf.y - a.cy;
+    const float pix_diff_x = pixfx - a.cx;
+    const float pix_diff_y = pixfy - a.cy;
     const float focal_x = a.focal_x, focal_y = a.focal_y, cx = a.cx, cy = a.cy;
     const int nb_src = a.nb_src;
     float median_intersected_depth = 0.0f;
@@ -405,11 +226,265 @@ __global__ void __launch_bounds__(256, 4) render_forward_kernel(const FwdArgs a)
   }
 }
 
+// PPL = pixels per lane.  PPL == 1: eight warps per tile, warp = 8x4 pixels.  PPL == 2: four warps per tile, warp =
+// 8x8 pixels, lane = the two pixels (x, y) and (x, y + 4): half as many warps pay the per-step overhead (record fetch,
+// cull, vote) of a tile, and the two pixels' blend chains interleave.  Per-pixel arithmetic and order are unchanged.
+template <int MODE, int BL, int PPL>
+__global__ void __launch_bounds__(256 / PPL, PPL == 1 ? 4 : 4) render_forward_kernel(const FwdArgs a) {
+  constexpr int BEFORE = (BL + 1) / 2;  // forward.cu:384
+  constexpr int BELOW = BL - BEFORE;    // forward.cu:385
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int NW = 8 / PPL;
+
+  // per-warp double buffer: [warp][buf][quad][lane]
+  __shared__ float4 s_rec[NW][2][4][32];
+  __shared__ float s_ref_to_src[MAX_SRC * 16];
+  __shared__ float s_src_cam_pos[MAX_SRC * 3];
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int W = a.W, H = a.H;
+  // warp w -> 8 x (4 PPL) sub-tile (2 across); lane -> pixel(s) inside it
+  const int sub_x0 = blockIdx.x * TILE + (warp & 1) * 8;
+  const int sub_y0 = blockIdx.y * TILE + (warp >> 1) * 4 * PPL;
+  const unsigned px = (unsigned)(sub_x0 + (lane & 7));
+  const float pixfx = (float)px;
+  const float rayx = (pixfx - a.cx) / a.focal_x;  // forward.cu:352
+  unsigned py[PPL];
+  uint32_t pix_id[PPL];
+  float pixfy[PPL], rayy[PPL];
+  bool inside[PPL], done[PPL];
+#pragma unroll
+  for (int q = 0; q < PPL; q++) {
+    py[q] = (unsigned)(sub_y0 + (lane >> 3) + 4 * q);
+    // blockIdx.z = view of a batched depth-only launch (0 otherwise): its tile ranges and output plane follow view z-1's
+    pix_id[q] = (MODE == MODE_DEPTH ? blockIdx.z * (uint32_t)(W * H) : 0u) + W * py[q] + px;
+    pixfy[q] = (float)py[q];
+    rayy[q] = (pixfy[q] - a.cy) / a.focal_y;
+    inside[q] = px < (unsigned)W && py[q] < (unsigned)H;
+    done[q] = !inside[q];
+  }
+
+  // sub-tile bounds for the cull test
+  const float wx0 = (float)sub_x0, wx1 = (float)(sub_x0 + 7);
+  const float wy0 = (float)sub_y0, wy1 = (float)(sub_y0 + 4 * PPL - 1);
+
+  const uint2 range = a.ranges[((MODE == MODE_DEPTH ? blockIdx.z * gridDim.y : 0u) + blockIdx.y) * gridDim.x + blockIdx.x];
+  const int total = (int)(range.y - range.x);
+
+  if (MODE == MODE_GEO) {
+    if (tid < a.nb_src * 16) s_ref_to_src[tid] = a.ref_to_src_list[tid];
+    if (tid < a.nb_src * 3) s_src_cam_pos[tid] = a.src_cam_pos[tid];
+    __syncthreads();  // the only CTA barrier: epilogue constants
+  }
+
+  const float epsilon = 1.0e-8f;
+  float T[PPL];
+  uint32_t last_contributor[PPL];
+  float C[PPL][3], normal_accum[PPL][3];
+  float zb[PPL][BL], wb[PPL][BL], db[PPL][BL];   // GEO: zb = depth denominator, db = plane distance; DEPTH: zb = depth
+  uint32_t cb[PPL][BL];
+  int before_ptr[PPL], below_count[PPL];
+  float total_buffer_weight[PPL], weighted_depth_sum[PPL];
+  // depth-only with BELOW==0 (BL==1): the reference `break`s out of the current 256-instance batch only
+  // (forward.cu:484-488) and resumes with the next one
+  bool brk[PPL];
+#pragma unroll
+  for (int q = 0; q < PPL; q++) {
+    T[q] = 1.0f;
+    last_contributor[q] = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { C[q][i] = 0.f; normal_accum[q][i] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < BL; k++) { zb[q][k] = 0.f; wb[q][k] = 0.f; db[q][k] = 0.f; cb[q][k] = 0u; }
+    before_ptr[q] = 0;
+    below_count[q] = 0;
+    total_buffer_weight[q] = 0.0f;
+    weighted_depth_sum[q] = 0.0f;
+    brk[q] = false;
+  }
+
+  const uint32_t* plist = a.point_list + range.x;
+  const int nchunks = (total + 31) >> 5;
+  float4(*wrec)[4][32] = s_rec[warp];
+
+  bool all_done = true;
+#pragma unroll
+  for (int q = 0; q < PPL; q++) all_done = all_done && done[q];
+
+  // software pipeline: ids two steps ahead (register), records one step ahead (cp.async)
+  uint32_t id_issue = (lane < total) ? plist[lane] : 0u;
+  if (nchunks > 0 && !__all_sync(FULL, all_done)) {
+    if (lane < total) {
+      const float4* r = a.rec + 4 * (size_t)id_issue;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (k < 3 || MODE != MODE_COLOR) cp_async16(&wrec[0][k][lane], r + k);
+    }
+    cp_async_commit();
+    id_issue = (32 + lane < total) ? plist[32 + lane] : 0u;
+
+    for (int c = 0; c < nchunks; c++) {
+      const int buf = c & 1;
+      const int c0 = c << 5;
+      if (c + 1 < nchunks) {
+        if (c0 + 32 + lane < total) {
+          const float4* r = a.rec + 4 * (size_t)id_issue;
+#pragma unroll
+          for (int k = 0; k < 4; k++)
+            if (k < 3 || MODE != MODE_COLOR) cp_async16(&wrec[buf ^ 1][k][lane], r + k);
+        }
+        id_issue = (c0 + 64 + lane < total) ? plist[c0 + 64 + lane] : 0u;
+      }
+      cp_async_commit();
+      cp_async_wait<1>();   // everything but the newest group has landed -> step c is in shared memory
+      __syncwarp();
+      if ((c0 & (TILE_PIX - 1)) == 0) {  // new 256-instance batch of the reference
+#pragma unroll
+        for (int q = 0; q < PPL; q++) brk[q] = false;
+      }
+
+      const int j = c0 + lane;
+      bool keep = false;
+      if (j < total) {
+        const float4 q0 = wrec[buf][0][lane];
+        const float4 q1 = wrec[buf][1][lane];
+        keep = subtile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, wx0, wx1, wy0, wy1);
+      }
+      unsigned m = __ballot_sync(FULL, keep);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t contributor = (uint32_t)(c0 + b + 1);  // forward.cu:417
+        const float4 g0 = wrec[buf][0][b];
+        const float4 g1 = wrec[buf][1][b];
+        const float dx = g0.x - pixfx;
+#pragma unroll
+        for (int q = 0; q < PPL; q++) {
+          // (nested ifs instead of `continue`: the q loop must unroll completely so that the per-pixel arrays stay
+          // in registers)
+          const float dy = g0.y - pixfy[q];
+          // con_o = (g0.z, g0.w, g1.x, g1.y); forward.cu:421-427
+          const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+          const float alpha = min(0.99f, g1.y * exp_power(power));
+          const float test_T = T[q] * (1.0f - alpha);
+          const bool blend = !(done[q] || brk[q]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+          if (blend && test_T < 0.0001f) done[q] = true;
+          if (blend && !(test_T < 0.0001f)) {
+          const float aT = alpha * T[q];
+
+          const float4 g2 = wrec[buf][2][b];
+          if (MODE != MODE_DEPTH) {
+            C[q][0] += g2.x * aT;
+            C[q][1] += g2.y * aT;
+            C[q][2] += g2.z * aT;
+          }
+          if (MODE != MODE_COLOR) {
+            const float4 g3 = wrec[buf][3][b];
+            // forward.cu:439-442: intersected_depth = -d / (n.ray + eps)
+            const float z_den = g3.x * rayx + g3.y * rayy[q] + g3.z + epsilon;
+            if (MODE == MODE_GEO) {
+              normal_accum[q][0] += g3.x * aT;
+              normal_accum[q][1] += g3.y * aT;
+              normal_accum[q][2] += g3.z * aT;
+              // The ring only ever needs the depths of the entries it still holds at the end, so the IEEE
+              // division is postponed to the epilogue: the ring stores the denominator (the numerator -d is
+              // re-read there).  "depth > 0" is decided from the operand signs: -d/den > 0 <=> d and den are
+              // non-zero with opposite signs (den = 0 gives +-inf of the wrong sign or NaN, NaN compares false;
+              // the quotient cannot underflow to 0 for finite plane parameters and a ray inside the frustum).
+              const bool need = (T[q] > 0.5f) || (below_count[q] < BELOW);
+              const bool z_pos = (g2.w > 0.0f && z_den < 0.0f) || (g2.w < 0.0f && z_den > 0.0f);
+              if (need && z_pos) {
+                if (T[q] > 0.5f) {
+#pragma unroll
+                  for (int k = 0; k < BEFORE; k++) {   // selects, not indexed stores: the ring must stay in registers
+                    const bool hit = before_ptr[q] == k;
+                    zb[q][k] = hit ? z_den : zb[q][k];
+                    db[q][k] = hit ? g2.w : db[q][k];
+                    wb[q][k] = hit ? aT : wb[q][k];
+                    cb[q][k] = hit ? contributor : cb[q][k];
+                  }
+                  before_ptr[q] = (before_ptr[q] + 1) % BEFORE;
+                } else {
+#pragma unroll
+                  for (int k = 0; k < BELOW; k++) {
+                    const bool hit = below_count[q] == k;
+                    zb[q][BEFORE + k] = hit ? z_den : zb[q][BEFORE + k];
+                    db[q][BEFORE + k] = hit ? g2.w : db[q][BEFORE + k];
+                    wb[q][BEFORE + k] = hit ? aT : wb[q][BEFORE + k];
+                    cb[q][BEFORE + k] = hit ? contributor : cb[q][BEFORE + k];
+                  }
+                  below_count[q]++;
+                }
+              }
+            } else {  // MODE_DEPTH, forward.cu:466-489
+              const float intersected_depth = -g2.w / z_den;
+              if (intersected_depth > 0.0f) {
+                if (T[q] > 0.5f) {
+                  // The depth-only ring is only ever consulted for the entry it evicts, so it is kept as a shift
+                  // register (newest entry in slot 0, the evicted one falls out of slot BEFORE-1; empty slots hold
+                  // weight 0) instead of the reference's cyclic pointer: same evicted values in the same order, and
+                  // no dynamically indexed array (which the compiler would place in local memory).
+                  const float old_w = wb[q][BEFORE - 1], old_z = zb[q][BEFORE - 1];
+#pragma unroll
+                  for (int k = BEFORE - 1; k > 0; k--) { zb[q][k] = zb[q][k - 1]; wb[q][k] = wb[q][k - 1]; }
+                  zb[q][0] = intersected_depth;
+                  wb[q][0] = aT;
+                  total_buffer_weight[q] -= old_w;
+                  weighted_depth_sum[q] -= old_w * old_z;
+                  total_buffer_weight[q] += aT;
+                  weighted_depth_sum[q] += aT * intersected_depth;
+                } else if (below_count[q] < BELOW) {
+                  below_count[q]++;
+                  total_buffer_weight[q] += aT;
+                  weighted_depth_sum[q] += aT * intersected_depth;
+                }
+                if (below_count[q] == BELOW) {
+                  // BELOW>0: T<=0.5 from here on, the sums are final -> the pixel is finished.
+                  // BELOW==0: reference semantics = leave this batch, resume at the next.
+                  if (BELOW > 0) done[q] = true; else brk[q] = true;
+                }
+              }
+            }
+          }
+          T[q] = test_T;
+          last_contributor[q] = contributor;
+          }
+        }
+      }
+      all_done = true;
+#pragma unroll
+      for (int q = 0; q < PPL; q++) all_done = all_done && done[q];
+      if (__all_sync(FULL, all_done)) break;   // warp-level early termination
+      __syncwarp();  // every lane is done reading buf before the step after next overwrites it (a vote is not a
+                     // memory-ordering barrier; compute-sanitizer racecheck flags the re-use without this)
+    }
+    cp_async_wait<0>();
+  }
+
+  const int HW = H * W;
+#pragma unroll
+  for (int q = 0; q < PPL; q++) {
+    if (inside[q])
+      render_forward_epilogue<MODE, BL>(a, s_ref_to_src, s_src_cam_pos, pix_id[q], pixfx, pixfy[q], HW, T[q],
+                                        last_contributor[q], C[q], normal_accum[q], zb[q], wb[q], db[q], cb[q],
+                                        total_buffer_weight[q], weighted_depth_sum[q]);
+  }
+}
+
+// average tile-list length from which the two-pixels-per-lane variant is used (see render_backward.cu)
+constexpr long long FWD_DENSE_LIST = 512;
+int g_fwd_variant = 0;   // 0 = choose per view, 1 / 2 = forced (ibgs_set_forward_variant)
+
 template <int MODE>
-int dispatch_bl(int BL, dim3 grid, cudaStream_t s, const FwdArgs& fa) {
+int dispatch_bl(int BL, dim3 grid, cudaStream_t s, const FwdArgs& fa, bool two_per_lane) {
   switch (BL) {
-#define CASE_BL(n) \
-  case n: render_forward_kernel<MODE, n><<<grid, 256, 0, s>>>(fa); break;
+#define CASE_BL(n)                                                                              \
+  case n:                                                                                       \
+    if (two_per_lane) render_forward_kernel<MODE, n, 2><<<grid, 128, 0, s>>>(fa);               \
+    else render_forward_kernel<MODE, n, 1><<<grid, 256, 0, s>>>(fa);                            \
+    break;
     CASE_BL(1) CASE_BL(2) CASE_BL(3) CASE_BL(4) CASE_BL(5) CASE_BL(6) CASE_BL(7) CASE_BL(8)
 #undef CASE_BL
     default:
@@ -419,10 +494,27 @@ int dispatch_bl(int BL, dim3 grid, cudaStream_t s, const FwdArgs& fa) {
   return IBGS_OK;
 }
 
+// Measured (3M Gaussians @1080p): the two-pixel variant wins in depth-only mode on long tile lists (render stage of
+// 4 batched views 0.98 -> 0.84 ms) and LOSES in render_geo / colour mode (1.97 -> 2.31 ms: 106 registers, and the
+// texture-bound epilogue runs twice per lane on half as many warps), so only depth-only launches take it by default.
+bool forward_two_per_lane(int mode, long long R, dim3 grid, int views) {
+  if (g_fwd_variant) return g_fwd_variant == 2;
+  return mode == MODE_DEPTH && R > FWD_DENSE_LIST * (long long)grid.x * grid.y * views;
+}
+
 }  // namespace
 
+extern "C" int ibgs_set_forward_variant(int pixels_per_lane) {
+  if (pixels_per_lane < 0 || pixels_per_lane > 2) {
+    ibgs_set_error("pixels_per_lane must be 0 (choose per view), 1 or 2, got %d", pixels_per_lane);
+    return IBGS_EINVAL;
+  }
+  g_fwd_variant = pixels_per_lane;
+  return IBGS_OK;
+}
+
 int launch_render_forward(const IbgsForwardArgs& f, const GeomState& g, const ImageState& im,
-                          const BinningState& b, TexPair tex, float focal_x, float focal_y, dim3 grid,
+                          const BinningState& b, TexPair tex, float focal_x, float focal_y, dim3 grid, int64_t R,
                           cudaStream_t s) {
   FwdArgs fa;
   fa.ranges = im.ranges;
@@ -460,16 +552,18 @@ int launch_render_forward(const IbgsForwardArgs& f, const GeomState& g, const Im
   fa.out_mask = f.out_use_first_src_frame;
 
   int rc;
+  const bool two = forward_two_per_lane(f.view.render_geo ? MODE_GEO : (f.view.render_depth_only ? MODE_DEPTH : MODE_COLOR), R, grid, 1);
   ProfScope prof(PROF_RENDER_FWD, s);
   // the reference evaluates render_geo before render_depth_only inside one kernel; with both set it
   // does both (forward.cu:445,466).  That combination is never produced by the callers
   // (gaussian_renderer/__init__.py:94-116,277-299); render_geo wins here.
   if (f.view.render_geo)
-    rc = dispatch_bl<MODE_GEO>(f.view.buffer_length, grid, s, fa);
+    rc = dispatch_bl<MODE_GEO>(f.view.buffer_length, grid, s, fa, two);
   else if (f.view.render_depth_only)
-    rc = dispatch_bl<MODE_DEPTH>(f.view.buffer_length, grid, s, fa);
+    rc = dispatch_bl<MODE_DEPTH>(f.view.buffer_length, grid, s, fa, two);
   else {
-    render_forward_kernel<MODE_COLOR, 1><<<grid, 256, 0, s>>>(fa);
+    if (two) render_forward_kernel<MODE_COLOR, 1, 2><<<grid, 128, 0, s>>>(fa);
+    else render_forward_kernel<MODE_COLOR, 1, 1><<<grid, 256, 0, s>>>(fa);
     rc = IBGS_OK;
   }
   if (rc != IBGS_OK) return rc;
@@ -480,7 +574,8 @@ int launch_render_forward(const IbgsForwardArgs& f, const GeomState& g, const Im
 // ibgs_forward_depth_batch: V depth-only views in one launch (gridDim.z = V); ranges has V * tiles entries, rec holds
 // the V * P (view, Gaussian) records, out_depths is [V,1,H,W].
 int launch_render_depth_batch(const IbgsDepthBatchArgs& f, const GeomState& g, const uint2* ranges,
-                              const BinningState& b, float focal_x, float focal_y, dim3 grid, cudaStream_t s) {
+                              const BinningState& b, float focal_x, float focal_y, dim3 grid, int64_t R,
+                              cudaStream_t s) {
   FwdArgs fa = {};
   fa.ranges = ranges;
   fa.point_list = b.point_list;
@@ -493,7 +588,8 @@ int launch_render_depth_batch(const IbgsDepthBatchArgs& f, const GeomState& g, c
   fa.cy = float(fa.H * 0.5f);
   fa.out_depth = f.out_depths;
   ProfScope prof(PROF_RENDER_FWD, s);
-  int rc = dispatch_bl<MODE_DEPTH>(f.buffer_length, dim3(grid.x, grid.y, (unsigned)f.V), s, fa);
+  int rc = dispatch_bl<MODE_DEPTH>(f.buffer_length, dim3(grid.x, grid.y, (unsigned)f.V), s, fa,
+                                   forward_two_per_lane(MODE_DEPTH, R, grid, f.V));
   if (rc != IBGS_OK) return rc;
   KERNEL_CHECK(f.debug, s);
   return IBGS_OK;

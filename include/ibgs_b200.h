@@ -315,11 +315,12 @@ void ibgs_profile_reset(void);
 int ibgs_profile_read(int stage, double* ms_total, int64_t* count);
 const char* ibgs_profile_name(int stage);
 int ibgs_profile_stages(void);
-/* Tuning knob for tests and experiments: the backward tile renderer exists in two variants -- one pixel per lane
+/* Tuning knobs for tests and experiments: each tile renderer exists in two variants -- one pixel per lane
  * (8 warps per tile) and two pixels per lane (4 warps per tile, one shared-memory reduction per 64 pixels) -- and
  * ibgs_backward picks per view by the average tile-list length.  0 restores that choice, 1 / 2 force a variant.
  * Results agree within the gradient gate either way (only the summation order differs). */
 int ibgs_set_backward_variant(int pixels_per_lane);
+int ibgs_set_forward_variant(int pixels_per_lane);   /* same knob for the forward tile renderer */
 /* Releases cached textures / arenas. */
 void ibgs_release_cached(void);
 

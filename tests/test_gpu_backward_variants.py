@@ -83,3 +83,44 @@ def test_ragged_image_and_buffer_lengths_with_two_pixels_per_lane(dpr, variant):
         _, g, _ = U.ours_forward_backward(dpr, sc, cot, buffer_length=bl, depth_error_threshold=0.05)
         for k in U.GRAD_NAMES:
             assert U.rel_l2(g[k], base[bl][k]) < 1e-4, (bl, k)
+
+
+@pytest.fixture()
+def fwd_variant():
+    from ibgs_b200 import _native as N
+
+    def force(v):
+        N.check(N.lib.ibgs_set_forward_variant(v), "ibgs_set_forward_variant")
+    yield force
+    N.lib.ibgs_set_forward_variant(0)
+
+
+@pytest.mark.parametrize("name,kw", [("cfg1", {}), ("tiny", dict(W=83, H=45))])
+def test_forward_variants_agree(dpr, fwd_variant, name, kw):
+    """One vs two pixels per lane in the forward tile renderer (by default only dense depth-only launches take the
+    second one): per-pixel blend order is the same, so integer outputs are identical and float outputs agree to
+    rounding (the two kernels contract a few shared products into FMAs differently) -- render_geo (buffer lengths
+    1..8), colour-only and depth-only, ragged image sizes included."""
+    sc = U.scene_to_device(S.make_scene(name, **kw))
+    fwd_variant(1)
+    sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
+    modes = [dict(render_geo=True, buffer_length=bl) for bl in (1, 2, 3, 4, 5, 8)]
+    modes += [dict(render_geo=False)] + [dict(render_geo=False, render_depth_only=True, buffer_length=bl) for bl in (1, 2, 3, 4, 7)]
+    ref = []
+    for m in modes:
+        outs, _, state = U.ours_forward_backward(dpr, sc, None, **m)
+        st = U.decode_ours(state)
+        ref.append((outs, st["final_T"].clone(), st["n_contrib"].clone()))
+    fwd_variant(2)
+    for m, (o1, T1, n1) in zip(modes, ref):
+        outs, _, state = U.ours_forward_backward(dpr, sc, None, **m)
+        st = U.decode_ours(state)
+        assert torch.equal(outs["radii"], o1["radii"])
+        assert (st["n_contrib"] != n1).float().mean().item() < 1e-4, m       # a pair exactly on a threshold may flip
+        assert (st["final_T"] - T1).abs().max().item() < 1e-5, m
+        for k in U.OUT_NAMES:
+            if k in ("radii", "mask"):
+                continue
+            d = (outs[k] - o1[k]).abs()
+            assert (d > 1e-4).float().mean().item() < 1e-3, (m, k, d.max().item())
+        assert (outs["mask"] != o1["mask"]).float().mean().item() < 1e-3, m

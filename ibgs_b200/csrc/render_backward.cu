@@ -307,8 +307,11 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // 8x8 pixels, lane = the two pixels (x, y) and (x, y + 4): the two pixels of a lane contribute to the SAME Gaussian, so
 // their 15 terms are added in registers and ONE shared-memory reduction serves 64 pixels instead of 32; the two
 // per-pixel dependency chains also interleave in the instruction stream.
+#ifndef IBGS_BWD_PPL2_CTAS
+#define IBGS_BWD_PPL2_CTAS 5   // 96 registers; measured 4 (120 regs): +1.4 %, 6 (80 regs, spills): +6 %
+#endif
 template <bool GEO, int MAXE, int NSRC, int PPL>
-__global__ void __launch_bounds__(256 / PPL, PPL == 1 ? 3 : 4) render_backward_pairs_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(256 / PPL, PPL == 1 ? 3 : IBGS_BWD_PPL2_CTAS) render_backward_pairs_kernel(const BwdArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
   constexpr int NW = 8 / PPL;  // warps per CTA (= per tile)
   // dynamic shared memory: record double buffers | reduction tiles | source-view matrices

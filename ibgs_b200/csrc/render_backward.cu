@@ -592,10 +592,11 @@ __global__ void __launch_bounds__(256 / PPL, PPL == 1 ? 3 : IBGS_BWD_PPL2_CTAS) 
 constexpr int bwd_smem_bytes(int ppl) {
   return (8 / ppl) * (2 * 4 * 32 * 16 + RED_WARP_FLOATS * 4) + MAX_SRC * 16 * 4;
 }
-// average tile-list length from which the 2-pixels-per-lane variant wins (measured: 126 instances per tile -> 8 %
-// slower, 1894 per tile -> 9 % faster; short lists are dominated by the per-pixel set-up and phase B, which the
-// 4-warp CTAs serialise)
-constexpr long long BWD_DENSE_LIST = 512;
+// average tile-list length from which the 2-pixels-per-lane variant is taken.  Measured at 1080p (forward+backward per
+// view, one / two pixels per lane): uniform scene 25 instances per tile 1.35 / 1.45 ms, 126: 2.07 / 2.14, 504: 4.28 /
+// 4.25; scene with a dense centre 158: 2.37 / 2.32, 315: 3.25 / 3.04, 630: 4.21 / 3.90, 1894: 5.14 / 4.73.  Short
+// lists are dominated by the per-pixel set-up and phase B, which the 4-warp CTAs serialise.
+constexpr long long BWD_DENSE_LIST = 256;
 int g_bwd_variant = IBGS_BWD_PPL;   // 0 = choose per view, 1 / 2 = forced (ibgs_set_backward_variant)
 
 inline int max_entries(int buffer_length) { return buffer_length <= 4 ? 5 : 9; }

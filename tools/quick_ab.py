@@ -39,13 +39,14 @@ def main():
     ap.add_argument("--depth-only", action="store_true", help="time the depth-only forward (render.py's source-depth renders)")
     ap.add_argument("--depth-batch", type=int, default=0, metavar="V",
                     help="time V source-view depth renders: V single calls vs one ibgs_forward_depth_batch call")
+    ap.add_argument("--P", type=int, default=0, help="override the number of Gaussians of the scene")
     ap.add_argument("--bwd-variant", type=int, default=0, help="force the backward variant (1 / 2 pixels per lane; 0 = automatic)")
     a = ap.parse_args()
     if a.bwd_variant:
         from ibgs_b200 import _native as _N
         _N.check(_N.lib.ibgs_set_backward_variant(a.bwd_variant), "ibgs_set_backward_variant")
     t0 = time.time()
-    sc = U.scene_to_device(S.make_scene(a.name))
+    sc = U.scene_to_device(S.make_scene(a.name, P=a.P or None))
     sc["src_rendered_depths"] = U.render_src_depths(dpr, sc)
     cot = {k: v.cuda() for k, v in S.cotangents(sc).items()}
     print(f"scene {a.name}: P={sc['P']} {sc['W']}x{sc['H']} built in {time.time()-t0:.1f}s", flush=True)

@@ -170,7 +170,8 @@ class OursRunner:
         am = sc["all_map"].detach().requires_grad_(True)
         res = dpr.GaussianRasterizer(rs)(means3D=self.leaf["means3D"], means2D=self.m2d, means2D_abs=self.m2a,
                                          opacities=self.leaf["opacities"], shs=self.leaf["shs"],
-                                         scales=self.leaf["scales"], rotations=self.leaf["rotations"], all_map=am)
+                                         scales=self.leaf["scales"], rotations=self.leaf["rotations"], all_map=am,
+                                         accumulate_grads=True)   # gradients add into the arena-backed .grad in-kernel
         cot = self.wl.cot
         torch.autograd.backward([res[0], res[2], res[3], res[5]],
                                 [cot["color"], cot["normal"], cot["depth"], cot["warped"]])
@@ -456,7 +457,7 @@ def train_step_timing(wl, impl, steps=4, warmup=3):
             rs = U.make_settings(wl.dpr, scv, render_geo=True)
             res = wl.dpr.GaussianRasterizer(rs)(means3D=pr["xyz"], means2D=z, means2D_abs=z, opacities=opacity,
                                                 shs=pr["f_dc"], shs_rest=pr["f_rest"], scales=scales,
-                                                rotations=rotations, all_map=all_map)
+                                                rotations=rotations, all_map=all_map, accumulate_grads=True)
             return res[0], res[2], res[3], res[5]
 
         def finish():

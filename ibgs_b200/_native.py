@@ -58,8 +58,12 @@ class IbgsBackwardArgs(C.Structure):
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dmeans2D_abs", _fp), ("dL_dcolors", _fp),
         ("dL_dopacity", _fp), ("dL_dcov3D", _fp), ("dL_dsh", _fp), ("dL_dsh_rest", _fp), ("dL_dscales", _fp),
         ("dL_drotations", _fp), ("dL_dall_map", _fp),
-        ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p),
+        ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p), ("accumulate_mask", C.c_uint32),
     ]
+
+
+ACC_MEANS3D, ACC_MEANS2D, ACC_MEANS2D_ABS, ACC_OPACITY, ACC_SH, ACC_SH_REST, ACC_SCALES, ACC_ROTATIONS, ACC_ALL_MAP = \
+    (1 << i for i in range(9))
 
 
 class IbgsPrologueArgs(C.Structure):

@@ -53,7 +53,15 @@ struct PBArgs {
   float* dL_dscales;
   float* dL_drotations;
   float* dL_dall_map;
+  unsigned acc;   // IBGS_ACC_* bits: outputs that are accumulated into (+=) instead of written
 };
+
+// gradient output word: plain store, or += when the caller asked for accumulation into this output
+// (IbgsBackwardArgs.accumulate_mask: gradient accumulation over a view batch without a separate add pass)
+template <bool ACC>
+__device__ __forceinline__ void put(float* p, float v, unsigned acc, unsigned bit) {
+  if (ACC && (acc & bit)) *p += v; else *p = v;
+}
 
 // reference auxiliary.h:111-121
 __forceinline__ __device__ float3 dnormvdv(float3 v, float3 dv) {
@@ -66,28 +74,32 @@ __forceinline__ __device__ float3 dnormvdv(float3 v, float3 dv) {
   return r;
 }
 
+template <bool ACC>
 __forceinline__ __device__ void write_zero_row(const PBArgs& a, int idx) {
+  const unsigned acc = ACC ? a.acc : 0u;   // accumulated outputs keep their value for a culled Gaussian
   float* p;
-  p = a.dL_dmeans3D + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f;
-  p = a.dL_dmeans2D + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f;
-  p = a.dL_dmeans2D_abs + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f;
+  if (!(acc & IBGS_ACC_MEANS3D)) { p = a.dL_dmeans3D + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f; }
+  if (!(acc & IBGS_ACC_MEANS2D)) { p = a.dL_dmeans2D + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f; }
+  if (!(acc & IBGS_ACC_MEANS2D_ABS)) { p = a.dL_dmeans2D_abs + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f; }
   p = a.dL_dcolors + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f;
-  a.dL_dopacity[idx] = 0.f;
+  if (!(acc & IBGS_ACC_OPACITY)) a.dL_dopacity[idx] = 0.f;
   if (a.dL_dcov3D) {
     p = a.dL_dcov3D + 6 * (size_t)idx;
     for (int i = 0; i < 6; i++) p[i] = 0.f;
   }
-  p = a.dL_dscales + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f;
-  reinterpret_cast<float4*>(a.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  p = a.dL_dall_map + 5 * (size_t)idx;
-  for (int i = 0; i < 5; i++) p[i] = 0.f;
+  if (!(acc & IBGS_ACC_SCALES)) { p = a.dL_dscales + 3 * (size_t)idx; p[0] = p[1] = p[2] = 0.f; }
+  if (!(acc & IBGS_ACC_ROTATIONS)) reinterpret_cast<float4*>(a.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!(acc & IBGS_ACC_ALL_MAP)) {
+    p = a.dL_dall_map + 5 * (size_t)idx;
+    for (int i = 0; i < 5; i++) p[i] = 0.f;
+  }
 }
 
 // warp-cooperative copy between a contiguous block of 32 global rows of `Lsrc` words (16-byte aligned because it
 // starts at a multiple of 32 rows) and columns [col0, col0 + Lsrc) of the warp's shared-memory tile (row stride Ls
 // words).  The block is moved as float4 (fully coalesced 512-byte requests); word i of the block belongs to row
 // i / Lsrc, computed with a multiply-high (`magic` = floor(2^32 / Lsrc) + 1, exact for i < 2^16).
-template <bool STORE>
+template <int STORE>   // 0: global -> tile, 1: tile -> global, 2: global += tile
 __device__ __forceinline__ void tile_copy(float* tile, float* gblock, int nwords, int Lsrc, int Ls, int col0,
                                           uint32_t magic, bool vec_ok, int lane) {
   const int pad = Ls - Lsrc;
@@ -101,7 +113,10 @@ __device__ __forceinline__ void tile_copy(float* tile, float* gblock, int nwords
     int t[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) t[j] = i + j + pad * (int)__umulhi((uint32_t)(i + j), magic);
-    if (STORE) {
+    if (STORE == 2) {
+      const float4 o = g4[i4];
+      g4[i4] = make_float4(o.x + tile[t[0]], o.y + tile[t[1]], o.z + tile[t[2]], o.w + tile[t[3]]);
+    } else if (STORE == 1) {
       g4[i4] = make_float4(tile[t[0]], tile[t[1]], tile[t[2]], tile[t[3]]);
     } else {
       const float4 v = g4[i4];
@@ -110,13 +125,15 @@ __device__ __forceinline__ void tile_copy(float* tile, float* gblock, int nwords
   }
   for (int i = (nvec << 2) + lane; i < nwords; i += 32) {  // partial last block (P not a multiple of 32)
     const int t = i + pad * (int)__umulhi((uint32_t)i, magic);
-    if (STORE) gblock[i] = tile[t]; else tile[t] = gblock[i];
+    if (STORE == 2) gblock[i] += tile[t]; else if (STORE == 1) gblock[i] = tile[t]; else tile[t] = gblock[i];
   }
 }
 
 // everything for one visible Gaussian; `shrow` is its SH row in the warp's shared-memory tile: coefficients on
 // entry, their gradient on exit (every word of the row is overwritten)
+template <bool ACC>
 __device__ __forceinline__ void preprocess_backward_one(const PBArgs& a, int idx, float* shrow) {
+  const unsigned acc = ACC ? a.acc : 0u;
   // slots 0-6 arrive unscaled from the tile renderer (render_backward.cu): apply 0.5*W, 0.5*H
   // (backward.cu:606-607) and the -0.5 of the conic terms (:799-801) once per Gaussian
   float4 a0 = a.arena[4 * (size_t)idx + 0];
@@ -128,12 +145,15 @@ __device__ __forceinline__ void preprocess_backward_one(const PBArgs& a, int idx
 
   // straight copies of what the renderer accumulated
   {
-    float* p = a.dL_dmeans2D + 3 * (size_t)idx; p[0] = a0.x; p[1] = a0.y; p[2] = 0.f;
-    p = a.dL_dmeans2D_abs + 3 * (size_t)idx; p[0] = a0.z; p[1] = a0.w; p[2] = 0.f;
+    float* p = a.dL_dmeans2D + 3 * (size_t)idx;
+    put<ACC>(p, a0.x, acc, IBGS_ACC_MEANS2D); put<ACC>(p + 1, a0.y, acc, IBGS_ACC_MEANS2D); put<ACC>(p + 2, 0.f, acc, IBGS_ACC_MEANS2D);
+    p = a.dL_dmeans2D_abs + 3 * (size_t)idx;
+    put<ACC>(p, a0.z, acc, IBGS_ACC_MEANS2D_ABS); put<ACC>(p + 1, a0.w, acc, IBGS_ACC_MEANS2D_ABS); put<ACC>(p + 2, 0.f, acc, IBGS_ACC_MEANS2D_ABS);
     p = a.dL_dcolors + 3 * (size_t)idx; p[0] = a2.x; p[1] = a2.y; p[2] = a2.z;
-    a.dL_dopacity[idx] = a1.w;
+    put<ACC>(a.dL_dopacity + idx, a1.w, acc, IBGS_ACC_OPACITY);
     p = a.dL_dall_map + 5 * (size_t)idx;
-    p[0] = a3.x; p[1] = a3.y; p[2] = a3.z; p[3] = 0.f; p[4] = a2.w;
+    put<ACC>(p, a3.x, acc, IBGS_ACC_ALL_MAP); put<ACC>(p + 1, a3.y, acc, IBGS_ACC_ALL_MAP); put<ACC>(p + 2, a3.z, acc, IBGS_ACC_ALL_MAP);
+    put<ACC>(p + 3, 0.f, acc, IBGS_ACC_ALL_MAP); put<ACC>(p + 4, a2.w, acc, IBGS_ACC_ALL_MAP);
   }
 
   const float3 mean = {a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]};
@@ -358,7 +378,8 @@ __device__ __forceinline__ void preprocess_backward_one(const PBArgs& a, int idx
   }
   {
     float* p = a.dL_dmeans3D + 3 * (size_t)idx;
-    p[0] = dL_dmean_acc.x; p[1] = dL_dmean_acc.y; p[2] = dL_dmean_acc.z;
+    put<ACC>(p, dL_dmean_acc.x, acc, IBGS_ACC_MEANS3D); put<ACC>(p + 1, dL_dmean_acc.y, acc, IBGS_ACC_MEANS3D);
+    put<ACC>(p + 2, dL_dmean_acc.z, acc, IBGS_ACC_MEANS3D);
   }
 
   // ---- cov3D -> scale / rotation, backward.cu:375-438 ----
@@ -382,7 +403,8 @@ __device__ __forceinline__ void preprocess_backward_one(const PBArgs& a, int idx
     dscale.y = Rt.m[1][0] * dL_dMt.m[1][0] + Rt.m[1][1] * dL_dMt.m[1][1] + Rt.m[1][2] * dL_dMt.m[1][2];
     dscale.z = Rt.m[2][0] * dL_dMt.m[2][0] + Rt.m[2][1] * dL_dMt.m[2][1] + Rt.m[2][2] * dL_dMt.m[2][2];
     float* ps = a.dL_dscales + 3 * (size_t)idx;
-    ps[0] = dscale.x; ps[1] = dscale.y; ps[2] = dscale.z;
+    put<ACC>(ps, dscale.x, acc, IBGS_ACC_SCALES); put<ACC>(ps + 1, dscale.y, acc, IBGS_ACC_SCALES);
+    put<ACC>(ps + 2, dscale.z, acc, IBGS_ACC_SCALES);
 #pragma unroll
     for (int w = 0; w < 3; w++) {
       dL_dMt.m[0][w] *= s.x;
@@ -398,14 +420,19 @@ __device__ __forceinline__ void preprocess_backward_one(const PBArgs& a, int idx
            2 * z * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * y * (dL_dMt.m[2][2] + dL_dMt.m[0][0]);
     dq.w = 2 * r * (dL_dMt.m[0][1] - dL_dMt.m[1][0]) + 2 * x * (dL_dMt.m[2][0] + dL_dMt.m[0][2]) +
            2 * y * (dL_dMt.m[1][2] + dL_dMt.m[2][1]) - 4 * z * (dL_dMt.m[1][1] + dL_dMt.m[0][0]);
-    reinterpret_cast<float4*>(a.dL_drotations)[idx] = dq;  // gradient w.r.t. the un-normalised quaternion (:437)
+    float4* pq = reinterpret_cast<float4*>(a.dL_drotations) + idx;  // gradient w.r.t. the un-normalised quaternion (:437)
+    if (ACC && (acc & IBGS_ACC_ROTATIONS)) {
+      const float4 o = *pq;
+      dq = make_float4(o.x + dq.x, o.y + dq.y, o.z + dq.z, o.w + dq.w);
+    }
+    *pq = dq;
   } else {
-    float* ps = a.dL_dscales + 3 * (size_t)idx;
-    ps[0] = ps[1] = ps[2] = 0.f;
-    reinterpret_cast<float4*>(a.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!(acc & IBGS_ACC_SCALES)) { float* ps = a.dL_dscales + 3 * (size_t)idx; ps[0] = ps[1] = ps[2] = 0.f; }
+    if (!(acc & IBGS_ACC_ROTATIONS)) reinterpret_cast<float4*>(a.dL_drotations)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
+template <bool ACC>
 __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const PBArgs a) {
   extern __shared__ float s_tiles[];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -425,19 +452,19 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
   const bool vec = a.vec_ok != 0;
   if (has_sh && any_visible) {
     if (split) {
-      tile_copy<false>(tile, const_cast<float*>(a.shs) + row0 * 3, rows * 3, 3, Ls, 0, a.magic_dc, vec, lane);
+      tile_copy<0>(tile, const_cast<float*>(a.shs) + row0 * 3, rows * 3, 3, Ls, 0, a.magic_dc, vec, lane);
       if (L > 3)
-        tile_copy<false>(tile, const_cast<float*>(a.shs_rest) + row0 * (L - 3), rows * (L - 3), L - 3, Ls, 3,
+        tile_copy<0>(tile, const_cast<float*>(a.shs_rest) + row0 * (L - 3), rows * (L - 3), L - 3, Ls, 3,
                          a.magic_rest, vec, lane);
     } else {
-      tile_copy<false>(tile, const_cast<float*>(a.shs) + row0 * L, rows * L, L, Ls, 0, a.magic, vec, lane);
+      tile_copy<0>(tile, const_cast<float*>(a.shs) + row0 * L, rows * L, L, Ls, 0, a.magic, vec, lane);
     }
     __syncwarp();
   }
   if (visible) {
-    preprocess_backward_one(a, idx, tile + lane * Ls);
+    preprocess_backward_one<ACC>(a, idx, tile + lane * Ls);
   } else if (in_range) {
-    write_zero_row(a, idx);
+    write_zero_row<ACC>(a, idx);
     if (has_sh) {
       float* row = tile + lane * Ls;
       for (int k = 0; k < L; k++) row[k] = 0.f;
@@ -445,12 +472,18 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const P
   }
   if (has_sh) {
     __syncwarp();
+    // accumulated SH gradients: a block of 32 culled Gaussians has nothing to add
+    const bool acc_dc = ACC && (a.acc & IBGS_ACC_SH), acc_rest = ACC && (a.acc & IBGS_ACC_SH_REST);
     if (split) {
-      tile_copy<true>(tile, a.dL_dsh + row0 * 3, rows * 3, 3, Ls, 0, a.magic_dc, vec, lane);
-      if (L > 3)
-        tile_copy<true>(tile, a.dL_dsh_rest + row0 * (L - 3), rows * (L - 3), L - 3, Ls, 3, a.magic_rest, vec, lane);
+      if (acc_dc) { if (any_visible) tile_copy<2>(tile, a.dL_dsh + row0 * 3, rows * 3, 3, Ls, 0, a.magic_dc, vec, lane); }
+      else tile_copy<1>(tile, a.dL_dsh + row0 * 3, rows * 3, 3, Ls, 0, a.magic_dc, vec, lane);
+      if (L > 3) {
+        if (acc_rest) { if (any_visible) tile_copy<2>(tile, a.dL_dsh_rest + row0 * (L - 3), rows * (L - 3), L - 3, Ls, 3, a.magic_rest, vec, lane); }
+        else tile_copy<1>(tile, a.dL_dsh_rest + row0 * (L - 3), rows * (L - 3), L - 3, Ls, 3, a.magic_rest, vec, lane);
+      }
     } else {
-      tile_copy<true>(tile, a.dL_dsh + row0 * L, rows * L, L, Ls, 0, a.magic, vec, lane);
+      if (acc_dc) { if (any_visible) tile_copy<2>(tile, a.dL_dsh + row0 * L, rows * L, L, Ls, 0, a.magic, vec, lane); }
+      else tile_copy<1>(tile, a.dL_dsh + row0 * L, rows * L, L, Ls, 0, a.magic, vec, lane);
     }
   }
 }
@@ -497,9 +530,11 @@ int launch_preprocess_backward(const IbgsBackwardArgs& f, const GeomState& g, co
   a.dL_dscales = f.dL_dscales;
   a.dL_drotations = f.dL_drotations;
   a.dL_dall_map = f.dL_dall_map;
+  a.acc = f.accumulate_mask;
   ProfScope prof(PROF_PREPROCESS_BWD, s);
   const size_t smem = (size_t)PB_WARPS * 32 * ((a.M * 3) | 1) * sizeof(float);
-  preprocess_backward_kernel<<<(f.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, smem, s>>>(a);
+  if (a.acc) preprocess_backward_kernel<true><<<(f.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, smem, s>>>(a);
+  else preprocess_backward_kernel<false><<<(f.P + PB_THREADS - 1) / PB_THREADS, PB_THREADS, smem, s>>>(a);
   KERNEL_CHECK(f.view.debug, s);
   return IBGS_OK;
 }

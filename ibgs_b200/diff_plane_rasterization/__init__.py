@@ -31,29 +31,19 @@ def cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, means2D_abs, sh, colors_precomp, opacities, scales, rotations,
-                        cov3Ds_precomp, all_map, raster_settings, sh_rest=None):
+                        cov3Ds_precomp, all_map, raster_settings, sh_rest=None, accumulate_grads=False):
     return _RasterizeGaussians.apply(means3D, means2D, means2D_abs, sh, colors_precomp, opacities, scales,
-                                     rotations, cov3Ds_precomp, all_map, raster_settings, sh_rest)
+                                     rotations, cov3Ds_precomp, all_map, raster_settings, sh_rest, accumulate_grads)
 
 
-def _ptr(t):
-    """Device address of a tensor, or NULL for an absent (empty) one -- the reference's convention
-    (rasterizer_impl.cu:470,595,643; forward.cu:244,280)."""
-    if t is None or t.numel() == 0:
-        return None
-    return t.data_ptr()
-
-
-def _f32c(t, device):
-    if t is None:
-        return None
-    if t.numel() == 0:
-        return t
-    if t.device != device:
-        t = t.to(device)
-    if t.dtype != torch.float32:
-        t = t.float()
-    return t.contiguous()
+def _accumulable(t):
+    """A leaf whose .grad already exists as a dense float32 tensor of its own shape: autograd would run
+    `t.grad += returned gradient` as a separate pass; with accumulate_grads the kernel adds into t.grad itself."""
+    if not (isinstance(t, torch.Tensor) and t.is_leaf and t.requires_grad):
+        return False            # (.grad of a non-leaf must not even be looked at: torch warns)
+    g = t.grad
+    return (g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous()
+            and tuple(g.shape) == tuple(t.shape))
 
 
 class _Allocator:
@@ -112,7 +102,7 @@ def _fill_view(view, rs, device, sh_coeffs, keep):
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, means2D_abs, sh, colors_precomp, opacities, scales, rotations,
-                cov3Ds_precomp, all_maps, raster_settings, sh_rest=None):
+                cov3Ds_precomp, all_maps, raster_settings, sh_rest=None, accumulate_grads=False):
         rs = raster_settings
         if means3D.ndimension() != 2 or means3D.size(1) != 3:
             # rasterize_points.cu:69-71
@@ -225,6 +215,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         alloc.release()
 
         ctx.raster_settings = rs
+        # accumulate_grads (extension over the reference API): the original input tensors, so that backward can add into
+        # the .grad of those that are leaves with an allocated gradient (gradient accumulation over a view batch)
+        ctx.accum_inputs = dict(means3D=means3D, means2D=means2D, means2D_abs=means2D_abs, sh=sh, sh_rest=sh_rest,
+                                opacities=opacities, scales=scales, rotations=rotations,
+                                all_map=all_maps) if accumulate_grads else None
         ctx.num_rendered = num_rendered
         ctx.opacity_shape = tuple(opacities.shape)  # reference returns [P,1] (rasterize_points.cu:215)
         ctx.tex_token = (int(a.tex_generation_out), src_images_c, src_depths_c,
@@ -282,6 +277,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         dL_dscales = torch.empty((P, 3), **fopt)
         dL_drotations = torch.empty((P, 4), **fopt)
 
+        accumulated = set()   # inputs whose gradient the kernel added into .grad: autograd gets None for them
         if P != 0:
             alloc = _Allocator(device)
             keep = []
@@ -324,6 +320,20 @@ class _RasterizeGaussians(torch.autograd.Function):
             a.dL_dscales = dL_dscales.data_ptr()
             a.dL_drotations = dL_drotations.data_ptr()
             a.dL_dall_map = dL_dall_map.data_ptr()
+            mask = 0
+            if ctx.accum_inputs is not None:
+                for name, field, bit in (("means3D", "dL_dmeans3D", N.ACC_MEANS3D), ("means2D", "dL_dmeans2D", N.ACC_MEANS2D),
+                                         ("means2D_abs", "dL_dmeans2D_abs", N.ACC_MEANS2D_ABS),
+                                         ("opacities", "dL_dopacity", N.ACC_OPACITY), ("sh", "dL_dsh", N.ACC_SH),
+                                         ("sh_rest", "dL_dsh_rest", N.ACC_SH_REST), ("scales", "dL_dscales", N.ACC_SCALES),
+                                         ("rotations", "dL_drotations", N.ACC_ROTATIONS),
+                                         ("all_map", "dL_dall_map", N.ACC_ALL_MAP)):
+                    t = ctx.accum_inputs.get(name)
+                    if t is not None and t.numel() and _accumulable(t) and getattr(a, field):
+                        setattr(a, field, t.grad.data_ptr())
+                        mask |= bit
+                        accumulated.add(name)
+            a.accumulate_mask = mask
             a.alloc = alloc.fn
             a.alloc_user = None
 
@@ -353,19 +363,21 @@ class _RasterizeGaussians(torch.autograd.Function):
             alloc.release()
 
         need = ctx.needs_input_grad
+        acc = accumulated
         grads = (
-            dL_dmeans3D if need[0] else None,
-            dL_dmeans2D if need[1] else None,
-            dL_dmeans2D_abs if need[2] else None,
-            dL_dsh if (need[3] and M_sh) else None,
+            dL_dmeans3D if (need[0] and "means3D" not in acc) else None,
+            dL_dmeans2D if (need[1] and "means2D" not in acc) else None,
+            dL_dmeans2D_abs if (need[2] and "means2D_abs" not in acc) else None,
+            dL_dsh if (need[3] and M_sh and "sh" not in acc) else None,
             dL_dcolors if (need[4] and colors_precomp.numel()) else None,
-            dL_dopacity.view(ctx.opacity_shape) if need[5] else None,
-            dL_dscales if (need[6] and scales.numel()) else None,
-            dL_drotations if (need[7] and rotations.numel()) else None,
+            dL_dopacity.view(ctx.opacity_shape) if (need[5] and "opacities" not in acc) else None,
+            dL_dscales if (need[6] and scales.numel() and "scales" not in acc) else None,
+            dL_drotations if (need[7] and rotations.numel() and "rotations" not in acc) else None,
             dL_dcov3D if (need[8] and need_cov) else None,
-            dL_dall_map if (need[9] and all_maps.numel()) else None,
+            dL_dall_map if (need[9] and all_maps.numel() and "all_map" not in acc) else None,
             None,
-            dL_dsh_rest if (split_sh and len(need) > 11 and need[11]) else None,
+            dL_dsh_rest if (split_sh and len(need) > 11 and need[11] and "sh_rest" not in acc) else None,
+            None,
         )
         return grads
 
@@ -417,7 +429,7 @@ class GaussianRasterizer(nn.Module):
         return visible
 
     def forward(self, means3D, means2D, means2D_abs, opacities, shs=None, colors_precomp=None, scales=None,
-                rotations=None, cov3D_precomp=None, all_map=None, shs_rest=None):
+                rotations=None, cov3D_precomp=None, all_map=None, shs_rest=None, accumulate_grads=False):
         raster_settings = self.raster_settings
 
         if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
@@ -440,6 +452,9 @@ class GaussianRasterizer(nn.Module):
         if all_map is None:
             all_map = torch.Tensor([])
 
-        # shs_rest (not in the reference API): shs = _features_dc, shs_rest = _features_rest, read in place
+        # shs_rest (not in the reference API): shs = _features_dc, shs_rest = _features_rest, read in place.
+        # accumulate_grads (not in the reference API): inputs that are leaves with an allocated float32 .grad get their
+        # gradient ADDED into it by the backward kernel itself (what autograd's AccumulateGrad would do in a separate
+        # pass per tensor); every other input receives its gradient through autograd as usual.
         return rasterize_gaussians(means3D, means2D, means2D_abs, shs, colors_precomp, opacities, scales,
-                                   rotations, cov3D_precomp, all_map, raster_settings, shs_rest)
+                                   rotations, cov3D_precomp, all_map, raster_settings, shs_rest, accumulate_grads)

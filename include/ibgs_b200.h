@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IBGS_ABI_VERSION 2
+#define IBGS_ABI_VERSION 3
 
 /* Compile-time constants of the reference (cuda_rasterizer/config.h:15-19, auxiliary.h:21-23). */
 #define IBGS_NUM_CHANNELS 3
@@ -106,6 +106,12 @@ typedef struct IbgsForwardArgs {
 /* returns num_rendered (tile instances R) */
 int64_t ibgs_forward(IbgsForwardArgs* args, void* stream);
 
+enum {
+  IBGS_ACC_MEANS3D = 1u << 0, IBGS_ACC_MEANS2D = 1u << 1, IBGS_ACC_MEANS2D_ABS = 1u << 2, IBGS_ACC_OPACITY = 1u << 3,
+  IBGS_ACC_SH = 1u << 4, IBGS_ACC_SH_REST = 1u << 5, IBGS_ACC_SCALES = 1u << 6, IBGS_ACC_ROTATIONS = 1u << 7,
+  IBGS_ACC_ALL_MAP = 1u << 8
+};
+
 /* Backward.  Replaces CudaRasterizer::Rasterizer::backward (rasterizer_impl.cu:519-666) as called
  * by RasterizeGaussiansBackwardCUDA (rasterize_points.cu:162-271).  Every dL_* output is fully
  * written (no pre-zeroing needed), except that rows of Gaussians with radii==0 are written as 0. */
@@ -149,6 +155,9 @@ typedef struct IbgsBackwardArgs {
   float* dL_dall_map;     /* [P,5] */
   ibgs_alloc_fn alloc;    /* SCRATCH only (per-Gaussian accumulation arena, 64 B/Gaussian) */
   void* alloc_user;
+  uint32_t accumulate_mask; /* IBGS_ACC_* bits: these gradient outputs are accumulated into (dst += grad; rows of culled
+                               Gaussians untouched) instead of written -- gradient accumulation over a batch of views
+                               without autograd's separate add pass.  0 = the reference behaviour (every output written). */
 } IbgsBackwardArgs;
 
 int ibgs_backward(IbgsBackwardArgs* args, void* stream);

@@ -46,6 +46,26 @@ def _accumulable(t):
             and tuple(g.shape) == tuple(t.shape))
 
 
+def _ptr(t):
+    """Device address of a tensor, or NULL for an absent (empty) one -- the reference's convention
+    (rasterizer_impl.cu:470,595,643; forward.cu:244,280)."""
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t, device):
+    if t is None:
+        return None
+    if t.numel() == 0:
+        return t
+    if t.device != device:
+        t = t.to(device)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
 class _Allocator:
     """The C side asks for its state / scratch buffers through this callback -- the ctypes spelling of
     the reference's resizeFunctional lambdas (rasterize_points.cu:29-35)."""

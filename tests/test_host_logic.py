@@ -111,3 +111,21 @@ def test_shim_directory_provides_reference_import_names():
             "print('ok')")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_python_layer_helpers_exist():
+    """The wrapper's helpers that only GPU calls exercise must at least exist (guards against an edit removing them)."""
+    import ibgs_b200.diff_plane_rasterization as d
+    import ibgs_b200.depth_batch as db
+    import ibgs_b200.loss_utils as lu
+    import ibgs_b200.optim as op
+    import ibgs_b200.fused as fu
+    for mod, names in ((d, ("_ptr", "_f32c", "_Allocator", "_accumulable", "_fill_view", "rasterize_gaussians")),
+                       (db, ("render_depth_batch", "render_depth_views", "DepthBatchSettings")),
+                       (lu, ("ssim", "compute_photometric_ssim", "ssim2", "ssim_map")),
+                       (op, ("ArenaAdam",)), (fu, ("gaussian_prologue",))):
+        for n in names:
+            assert hasattr(mod, n), (mod.__name__, n)
+    import torch
+    assert d._ptr(None) is None and d._ptr(torch.empty(0)) is None
+    assert d._accumulable(torch.zeros(3)) is False

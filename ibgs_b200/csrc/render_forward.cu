@@ -24,10 +24,6 @@
 //     (the reference kernel carries a 192-byte local stack for it).
 #include "common.cuh"
 
-#ifndef IBGS_EXP
-#define IBGS_EXP 0
-#endif
-
 namespace {
 
 struct FwdArgs {
@@ -97,7 +93,7 @@ __device__ __forceinline__ void render_forward_epilogue(const FwdArgs& a, const 
   if (MODE == MODE_DEPTH) {
     a.out_depth[pix_id] = weighted_depth_sum / (total_buffer_weight + epsilon);  // forward.cu:508
   }
-  if (MODE == MODE_GEO && IBGS_EXP != 11) {
+  if (MODE == MODE_GEO) {
     // forward.cu:512-663
     const float inv_focal_x = 1.0f / a.focal_x;
     const float inv_focal_y = 1.0f / a.focal_y;
@@ -133,11 +129,7 @@ __device__ __forceinline__ void render_forward_epilogue(const FwdArgs& a, const 
             const bool in_bounds = (pp.x >= 0.0f && pp.x <= (float)(W - 1) && pp.y >= 0.0f &&
                                     pp.y <= (float)(H - 1));
             if (in_bounds) {
-#if IBGS_EXP == 10
-              const float4 texC = make_float4(pp.x, pp.y, 0.f, 0.f);
-#else
               const float4 texC = tex2DLayered<float4>(a.texColor, pp.x + 0.5f, pp.y + 0.5f, s);
-#endif
               warped_color_all[s * 3] += weight * texC.x;
               warped_color_all[s * 3 + 1] += weight * texC.y;
               warped_color_all[s * 3 + 2] += weight * texC.z;
@@ -189,11 +181,7 @@ __device__ __forceinline__ void render_forward_epilogue(const FwdArgs& a, const 
         const bool in_bounds = (pp.x >= 0.0f && pp.x <= (float)(W - 1) && pp.y >= 0.0f &&
                                 pp.y <= (float)(H - 1));
         float warped_depth = 0.0f;
-#if IBGS_EXP == 10
-        if (in_bounds) warped_depth = tz;
-#else
         if (in_bounds) warped_depth = tex2DLayered<float>(a.texDepth, pp.x + 0.5f, pp.y + 0.5f, s);
-#endif
         const float depth_error = fabsf(warped_depth - tz) * inv_z;
         if (warped_depth > 0.0f && depth_error < a.depth_error_threshold) {
           const float inv_weight = 1.0f / (total_w_src[s] + epsilon);

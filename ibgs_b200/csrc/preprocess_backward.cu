@@ -21,6 +21,11 @@ namespace {
 
 #define PB_THREADS 128
 #define PB_WARPS (PB_THREADS / 32)
+// 8 CTAs of 128 threads per SM = 64 registers (a few spilled words): the kernel is HBM-latency bound and wants the
+// warps -- measured in accumulate mode 0.54 ms at 96 registers, 0.41 at 80, 0.37 at 64, 0.45 at 48
+#ifndef PB_MIN_CTAS
+#define PB_MIN_CTAS 8
+#endif
 
 struct PBArgs {
   int P, D, M;
@@ -433,7 +438,7 @@ __device__ __forceinline__ void preprocess_backward_one(const PBArgs& a, int idx
 }
 
 template <bool ACC>
-__global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(const PBArgs a) {
+__global__ void __launch_bounds__(PB_THREADS, PB_MIN_CTAS) preprocess_backward_kernel(const PBArgs a) {
   extern __shared__ float s_tiles[];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;

@@ -88,22 +88,37 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
   }
 }
 
-// reference rasterizer_impl.cu:233-255 (on 32-bit tile ids instead of the high half of 64-bit keys)
+// reference rasterizer_impl.cu:233-255 (on 16- / 32-bit tile ids instead of the high half of 64-bit keys).  One thread
+// takes the 16 bytes of ids starting at a 16-byte boundary (8 uint16 or 4 uint32: one vector load) plus the id before
+// them; the reference's one-thread-per-instance form is launch- and tail-bound at 15 M instances.
 template <typename TileT>
-__global__ void identify_tile_ranges_kernel(int L, const TileT* __restrict__ tile_ids, uint2* ranges) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= L) return;
-  uint32_t currtile = tile_ids[idx];
-  if (idx == 0)
-    ranges[currtile].x = 0;
-  else {
-    uint32_t prevtile = tile_ids[idx - 1];
-    if (currtile != prevtile) {
-      ranges[prevtile].y = idx;
-      ranges[currtile].x = idx;
+__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(int L, const TileT* __restrict__ tile_ids, uint2* ranges) {
+  constexpr int PER = 16 / sizeof(TileT);
+  const int base = (blockIdx.x * blockDim.x + threadIdx.x) * PER;
+  if (base >= L) return;
+  TileT ids[PER];
+  if (base + PER <= L) {
+    *reinterpret_cast<uint4*>(ids) = *reinterpret_cast<const uint4*>(tile_ids + base);
+  } else {
+#pragma unroll
+    for (int k = 0; k < PER; k++) ids[k] = (base + k < L) ? tile_ids[base + k] : (TileT)0;
+  }
+  uint32_t prevtile = (base == 0) ? 0u : (uint32_t)tile_ids[base - 1];
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const int idx = base + k;
+    if (idx < L) {
+      const uint32_t currtile = ids[k];
+      if (idx == 0) {
+        ranges[currtile].x = 0;
+      } else if (currtile != prevtile) {
+        ranges[prevtile].y = idx;
+        ranges[currtile].x = idx;
+      }
+      if (idx == L - 1) ranges[currtile].y = L;
+      prevtile = currtile;
     }
   }
-  if (idx == L - 1) ranges[currtile].y = L;
 }
 
 // reference rasterizer_impl.cu:152-167
@@ -234,9 +249,9 @@ int run_binning_items(int P, const int* radii, int debug, int views, const GeomS
     CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)tiles_per_view * views * sizeof(uint2), s));
     if (R > 0) {
       if (narrow)
-        identify_tile_ranges_kernel<uint16_t><<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, t16_sorted, ranges);
+        identify_tile_ranges_kernel<uint16_t><<<(int)((R + 256 * 8 - 1) / (256 * 8)), 256, 0, s>>>((int)R, t16_sorted, ranges);
       else
-        identify_tile_ranges_kernel<uint32_t><<<(int)((R + 255) / 256), 256, 0, s>>>((int)R, sc.tiles_sorted, ranges);
+        identify_tile_ranges_kernel<uint32_t><<<(int)((R + 256 * 4 - 1) / (256 * 4)), 256, 0, s>>>((int)R, sc.tiles_sorted, ranges);
       KERNEL_CHECK(debug, s);
     }
   }

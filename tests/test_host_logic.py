@@ -129,3 +129,40 @@ def test_python_layer_helpers_exist():
     import torch
     assert d._ptr(None) is None and d._ptr(torch.empty(0)) is None
     assert d._accumulable(torch.zeros(3)) is False
+
+
+def test_fast_paths_fail_loudly_without_cuda_tensors():
+    """No CPU / PyTorch fallback anywhere: every optional fast path raises on CPU tensors instead of computing."""
+    import pytest
+    import torch
+    import ibgs_b200.depth_batch as db
+    import ibgs_b200.loss_utils as lu
+    import ibgs_b200.fused as fu
+    from ibgs_b200.optim import ArenaAdam
+    x = torch.rand((3, 16, 16))
+    with pytest.raises(RuntimeError):
+        lu.ssim(x, x)
+    with pytest.raises(NotImplementedError):
+        lu.ssim(x, x, window_size=7)
+    with pytest.raises(RuntimeError):
+        ArenaAdam({"w": torch.zeros(4)}, {"w": 0.1})
+    with pytest.raises(ValueError):
+        ArenaAdam({}, {})
+    P = 5
+    st = db.DepthBatchSettings(8, 8, 0.5, 0.5, 1.0, torch.eye(4)[None], torch.eye(4)[None], 4)
+    with pytest.raises(RuntimeError):
+        db.render_depth_batch(st, torch.zeros((P, 3)), torch.zeros((P, 1)), scales=torch.zeros((P, 3)),
+                              rotations=torch.zeros((P, 4)), all_maps=torch.zeros((1, P, 5)))
+    with pytest.raises(Exception):   # neither all_maps nor normals
+        db.render_depth_batch(st, torch.zeros((P, 3)), torch.zeros((P, 1)), scales=torch.zeros((P, 3)),
+                              rotations=torch.zeros((P, 4)))
+    with pytest.raises(RuntimeError):
+        fu.gaussian_prologue(torch.zeros((P, 3)), torch.zeros((P, 1)), torch.zeros((P, 3)), torch.zeros((P, 4)),
+                             torch.zeros((P, 1, 3)), torch.zeros((P, 8, 3)))
+
+
+def test_kernel_variant_knobs_validate_their_argument():
+    from ibgs_b200 import _native as N
+    for fn in (N.lib.ibgs_set_backward_variant, N.lib.ibgs_set_forward_variant):
+        assert fn(7) < 0 and "pixels_per_lane" in N.last_error()
+        assert fn(2) == 0 and fn(0) == 0

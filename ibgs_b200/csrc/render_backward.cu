@@ -21,11 +21,12 @@
 //   * the median-buffer terms (backward.cu:693-767: texture taps, per-view loops, per-pixel loads) touch
 //     at most buffer_length pairs per pixel but sit in the middle of the reference's pair loop, where they
 //     diverge the warp.  Here the pair loop only RECORDS those pairs (Gaussian id, T, colour/normal part of
-//     dL/dalpha) into a per-pixel list in global scratch; a SECOND kernel (render_backward_median_kernel, one
-//     thread per pixel, every lane busy with its own entries) evaluates their whole gradient and adds it with
-//     vector reductions.  Splitting the kernels keeps the 40-odd per-pixel registers of that phase out of the
-//     pair loop's register allocation (3 CTAs/SM instead of 2) and lets the texture-latency-bound phase run at
-//     its own, high occupancy.
+//     dL/dalpha) into a per-pixel list in global scratch; after the loop every lane walks its own pixels' lists
+//     (phase B, median_pair_backward) and adds their whole gradient with vector reductions.  Phase B runs as the
+//     tail of the same kernel: it is texture / dependent-load latency bound, and as a tail its waits overlap the
+//     pair loops of the other CTAs on the SM (a separate kernel for it was measured and is slower);
+//   * two variants (template PPL): one pixel per lane (8 warps per tile) or two pixels per lane (4 warps per tile,
+//     the two pixels' terms add in registers, one reduction per 64 pixels); launch_render_backward picks per view.
 // Summation order differs from the reference (which is itself run-to-run nondeterministic); the
 // parity gate for gradients is relative L2 <= 1e-3.
 #include "common.cuh"

@@ -20,8 +20,12 @@
 //     Gaussians are exactly ones the reference would skip at forward.cu:425 for all 32 pixels, so
 //     per-pixel results are unchanged;
 //   * warp-level early termination: a warp leaves as soon as its 32 pixels are done;
-//   * the median ring lives in registers (compile-time BL), not in a dynamically indexed local array
-//     (the reference kernel carries a 192-byte local stack for it).
+//   * the median ring lives in registers (compile-time BL, updates written as selects; the depth-only ring is a
+//     shift register), not in a dynamically indexed local array (the reference kernel carries a 192-byte local
+//     stack for it);
+//   * template PPL: one pixel per lane (8 warps per tile) or two pixels per lane (4 warps per tile, 8x8 pixels per
+//     warp); the second variant is taken for depth-only launches with long tile lists, where there is no epilogue
+//     to pay for twice per lane.
 #include "common.cuh"
 
 namespace {

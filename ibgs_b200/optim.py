@@ -60,6 +60,44 @@ class ArenaAdam:
         """Rebuild after densification / pruning from the new per-group tensors and their carried-over moments."""
         return cls(named_tensors, lrs, betas=betas, eps=eps, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq, step=step)
 
+    # ---- densification: the counterparts of GaussianModel's optimizer surgery (scene/gaussian_model.py:362-470) --------
+    # Each returns a NEW ArenaAdam (the arenas are re-laid-out; densification happens every 100 iterations, so this is
+    # off the per-step path) and keeps step_count, betas, eps and every group's current learning rate.
+    def _rebuild(self, tensors, exp_avg, exp_avg_sq):
+        lrs = {g["name"]: g["lr"] for g in self.param_groups}
+        return ArenaAdam(tensors, lrs, betas=self.betas, eps=self.eps, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq,
+                         step=self.step_count)
+
+    def prune(self, keep_mask):
+        """_prune_optimizer (scene/gaussian_model.py:377-395): rows (dim 0) of every group, and of both moments, where
+        keep_mask is True.  prune_points passes `~mask`."""
+        keep_mask = keep_mask.to(self.device)
+        t = {n: p.detach()[keep_mask] for n, p in self.params.items()}
+        m = {n: self.state(n)["exp_avg"][keep_mask] for n in self.params}
+        v = {n: self.state(n)["exp_avg_sq"][keep_mask] for n in self.params}
+        return self._rebuild(t, m, v)
+
+    def extend(self, tensors_dict):
+        """cat_tensors_to_optimizer (scene/gaussian_model.py:420-438): new rows appended to every group, their moments
+        start at zero."""
+        t, m, v = {}, {}, {}
+        for n, p in self.params.items():
+            ext = tensors_dict[n].to(device=self.device, dtype=torch.float32)
+            t[n] = torch.cat((p.detach(), ext), dim=0)
+            st = self.state(n)
+            m[n] = torch.cat((st["exp_avg"], torch.zeros_like(ext)), dim=0)
+            v[n] = torch.cat((st["exp_avg_sq"], torch.zeros_like(ext)), dim=0)
+        return self._rebuild(t, m, v)
+
+    def reset_state(self, name, tensor):
+        """replace_tensor_to_optimizer (scene/gaussian_model.py:362-375; the opacity reset): group `name` takes the
+        new values in place and its moments restart from zero."""
+        off, n = self._ranges[name]
+        self.flat_params[off:off + n].copy_(tensor.detach().reshape(-1))
+        self.exp_avg[off:off + n].zero_()
+        self.exp_avg_sq[off:off + n].zero_()
+        return self.params[name]
+
     def state(self, name):
         off, n = self._ranges[name]
         shape = self.params[name].shape

@@ -80,3 +80,68 @@ def test_grad_scale_partial_groups_and_errors():
                              {n: b.state(n)["exp_avg"] for n in init}, {n: b.state(n)["exp_avg_sq"] for n in init},
                              step=b.step_count)
     assert torch.equal(c.exp_avg, b.exp_avg) and torch.equal(c.flat_params, b.flat_params) and c.step_count == 1
+
+
+def test_densification_surgery_matches_the_reference_helpers():
+    """prune / extend / reset_state against the reference's optimizer surgery applied to torch.optim.Adam
+    (scene/gaussian_model.py:362-438, re-stated inline on the same state dict), then one more step on both."""
+    from ibgs_b200.optim import ArenaAdam
+    P = 200
+    init = _init(P, seed=3)
+    lrs = {n: lr for n, _, lr in GROUPS}
+    opt = ArenaAdam(init, lrs)
+    ref_p = {n: torch.nn.Parameter(init[n].clone()) for n in init}
+    ref = torch.optim.Adam([{"params": [ref_p[n]], "lr": lrs[n], "name": n} for n in init], lr=0.0, eps=1e-15)
+    g = torch.Generator().manual_seed(9)
+
+    def step_both():
+        for grp in ref.param_groups:
+            n = grp["name"]
+            gr = torch.randn(tuple(grp["params"][0].shape), generator=g).cuda()
+            grp["params"][0].grad = gr
+            opt.params[n].grad.copy_(gr)
+        ref.step()
+        opt.step(zero_grads=True)
+
+    def check():
+        for grp in ref.param_groups:
+            n, p = grp["name"], grp["params"][0]
+            assert torch.allclose(opt.params[n].detach(), p.detach(), rtol=0, atol=5e-6), n
+            # float32 moments: torch's multi-tensor kernels round a few operations differently (~1e-5 relative)
+            assert torch.allclose(opt.state(n)["exp_avg"], ref.state[p]["exp_avg"], rtol=1e-3, atol=1e-6), n
+            assert torch.allclose(opt.state(n)["exp_avg_sq"], ref.state[p]["exp_avg_sq"], rtol=1e-3, atol=1e-8), n
+
+    step_both(); step_both(); check()
+    # prune (_prune_optimizer)
+    keep = (torch.rand(P, generator=g) > 0.3).cuda()
+    for grp in ref.param_groups:
+        p = grp["params"][0]
+        st = ref.state.pop(p)
+        st["exp_avg"], st["exp_avg_sq"] = st["exp_avg"][keep], st["exp_avg_sq"][keep]
+        grp["params"][0] = torch.nn.Parameter(p.detach()[keep])
+        ref.state[grp["params"][0]] = st
+    opt = opt.prune(keep)
+    check(); step_both(); check()
+    # extend (cat_tensors_to_optimizer)
+    new = {n: torch.randn((17, w), generator=g).cuda() for n, w, _ in GROUPS}
+    for grp in ref.param_groups:
+        p, ext = grp["params"][0], new[grp["name"]]
+        st = ref.state.pop(p)
+        st["exp_avg"] = torch.cat((st["exp_avg"], torch.zeros_like(ext)), dim=0)
+        st["exp_avg_sq"] = torch.cat((st["exp_avg_sq"], torch.zeros_like(ext)), dim=0)
+        grp["params"][0] = torch.nn.Parameter(torch.cat((p.detach(), ext), dim=0))
+        ref.state[grp["params"][0]] = st
+    opt = opt.extend(new)
+    assert opt.step_count == 3 and opt.params["xyz"].shape[0] == int(keep.sum()) + 17
+    check(); step_both(); check()
+    # reset_state (replace_tensor_to_optimizer: the opacity reset)
+    newop = torch.full_like(opt.params["opacity"].detach(), -2.0)
+    for grp in ref.param_groups:
+        if grp["name"] == "opacity":
+            p = grp["params"][0]
+            st = ref.state.pop(p)
+            st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(newop), torch.zeros_like(newop)
+            grp["params"][0] = torch.nn.Parameter(newop.clone())
+            ref.state[grp["params"][0]] = st
+    opt.reset_state("opacity", newop)
+    check(); step_both(); check()

@@ -187,6 +187,10 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
     ibgs_set_error("render_geo / render_depth_only need all_map");
     return IBGS_EINVAL;
   }
+  if (!ibgs_aligned16(a->rotations)) {
+    ibgs_set_error("rotations must be 16-byte aligned (read as float4); pass an aligned copy");
+    return IBGS_EINVAL;
+  }
   const int W = v.image_width, H = v.image_height;
   const float focal_y = H / (2.0f * v.tanfovy);  // rasterizer_impl.cu:362-363
   const float focal_x = W / (2.0f * v.tanfovx);
@@ -288,6 +292,10 @@ extern "C" int64_t ibgs_forward_depth_batch(IbgsDepthBatchArgs* a, void* stream_
     ibgs_set_error("provide all_maps, or normals + camera_centers");
     return IBGS_EINVAL;
   }
+  if (!ibgs_aligned16(a->rotations)) {
+    ibgs_set_error("rotations must be 16-byte aligned (read as float4); pass an aligned copy");
+    return IBGS_EINVAL;
+  }
   if ((int64_t)P * V > 0x7fffffffLL) {
     ibgs_set_error("P*V = %lld exceeds the int32 item limit", (long long)P * V);
     return IBGS_ELIMIT;
@@ -376,6 +384,10 @@ extern "C" int ibgs_backward(IbgsBackwardArgs* a, void* stream_v) {
       !a->dL_dscales || !a->dL_drotations || !a->dL_dall_map || (a->shs && !a->dL_dsh) ||
       (a->shs && a->shs_rest && !a->dL_dsh_rest)) {
     ibgs_set_error("gradient output pointers must not be NULL");
+    return IBGS_EINVAL;
+  }
+  if (!ibgs_aligned16(a->rotations) || !ibgs_aligned16(a->dL_drotations)) {
+    ibgs_set_error("rotations / dL_drotations must be 16-byte aligned (accessed as float4); pass aligned tensors");
     return IBGS_EINVAL;
   }
   const int W = v.image_width, H = v.image_height;

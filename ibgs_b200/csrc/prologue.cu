@@ -173,6 +173,10 @@ extern "C" int ibgs_prologue_forward(const IbgsPrologueArgs* a, void* stream_v) 
     ibgs_set_error("output pointers must not be NULL");
     return IBGS_EINVAL;
   }
+  if (!ibgs_aligned16(a->rotation_raw) || !ibgs_aligned16(a->rotations)) {
+    ibgs_set_error("rotation_raw / rotations must be 16-byte aligned (they are accessed as float4)");
+    return IBGS_EINVAL;
+  }
   if (!a->normal_raw) p.all_map = nullptr;
   prologue_forward_kernel<<<(a->P + 255) / 256, 256, 0, s>>>(p);
   KERNEL_CHECK(0, s);
@@ -195,6 +199,10 @@ extern "C" int ibgs_prologue_backward(const IbgsPrologueArgs* a, void* stream_v)
       (with_sh && a->sh_rest > 0 && !a->d_features_rest) ||
       (a->normal_raw && (!a->d_normal_raw || !a->d_offset || !a->d_xyz))) {
     ibgs_set_error("gradient output pointers must not be NULL");
+    return IBGS_EINVAL;
+  }
+  if (!ibgs_aligned16(a->rotation_raw) || !ibgs_aligned16(a->g_rotations) || !ibgs_aligned16(a->d_rotation_raw)) {
+    ibgs_set_error("rotation_raw / g_rotations / d_rotation_raw must be 16-byte aligned (they are accessed as float4)");
     return IBGS_EINVAL;
   }
   prologue_backward_kernel<<<(a->P + 255) / 256, 256, 0, s>>>(p);

@@ -43,7 +43,7 @@ def _accumulable(t):
         return False            # (.grad of a non-leaf must not even be looked at: torch warns)
     g = t.grad
     return (g is not None and g.is_cuda and g.dtype == torch.float32 and g.is_contiguous()
-            and tuple(g.shape) == tuple(t.shape))
+            and tuple(g.shape) == tuple(t.shape) and g.data_ptr() % 16 == 0)   # (float4 stores into quaternion rows)
 
 
 def _ptr(t):
@@ -63,7 +63,12 @@ def _f32c(t, device):
         t = t.to(device)
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        # a view at an odd offset of a larger buffer (e.g. one group of a packed parameter arena): the kernels read
+        # quaternion rows as float4, so hand them a fresh (512-byte aligned) copy
+        t = t.clone()
+    return t
 
 
 class _Allocator:

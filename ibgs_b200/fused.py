@@ -25,7 +25,10 @@ def _c(t):
     t = t.detach()
     if t.dtype != torch.float32:
         t = t.float()
-    return t.contiguous()
+    t = t.contiguous()
+    if t.data_ptr() % 16:   # a slice at an odd offset of a packed arena: quaternion rows are accessed as float4
+        t = t.clone()
+    return t
 
 
 class _GaussianPrologue(torch.autograd.Function):

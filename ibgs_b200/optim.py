@@ -21,6 +21,8 @@ import torch
 
 from . import _native as N
 
+ARENA_ALIGN = 64   # floats: groups start on 256-byte boundaries
+
 
 class ArenaAdam:
     def __init__(self, named_tensors, lrs, betas=(0.9, 0.999), eps=1e-15, exp_avg=None, exp_avg_sq=None, step=0):
@@ -33,16 +35,22 @@ class ArenaAdam:
             raise RuntimeError("ibgs_b200.optim: parameters must be CUDA tensors (there is no CPU path)")
         self.device = first.device
         sizes = [int(t.numel()) for t in named_tensors.values()]
-        total = sum(sizes)
+        # every group starts on a 256-byte boundary of the arenas: the rasterizer / prologue kernels read and write some
+        # of these tensors (rotations and their gradients) with 16-byte vector accesses, and after densification the
+        # Gaussian count is arbitrary.  The pad words are zero in all four arenas and belong to no group.
+        starts, total = [], 0
+        for n in sizes:
+            total = (total + ARENA_ALIGN - 1) // ARENA_ALIGN * ARENA_ALIGN
+            starts.append(total)
+            total += n
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.flat_params = torch.empty(total, **f32)
+        self.flat_params = torch.zeros(total, **f32)
         self.flat_grads = torch.zeros(total, **f32)
         self.exp_avg = torch.zeros(total, **f32)
         self.exp_avg_sq = torch.zeros(total, **f32)
         self.betas, self.eps, self.step_count = (float(betas[0]), float(betas[1])), float(eps), int(step)
         self.params, self.grads, self.param_groups, self._ranges = OrderedDict(), OrderedDict(), [], OrderedDict()
-        off = 0
-        for (name, t), n in zip(named_tensors.items(), sizes):
+        for (name, t), n, off in zip(named_tensors.items(), sizes, starts):
             sl = slice(off, off + n)
             self.flat_params[sl].copy_(t.detach().reshape(-1))
             p = torch.nn.Parameter(self.flat_params[sl].view(t.shape), requires_grad=True)
@@ -53,7 +61,6 @@ class ArenaAdam:
             if exp_avg is not None and name in exp_avg:
                 self.exp_avg[sl].copy_(exp_avg[name].reshape(-1))
                 self.exp_avg_sq[sl].copy_(exp_avg_sq[name].reshape(-1))
-            off += n
 
     @classmethod
     def from_state(cls, named_tensors, lrs, exp_avg, exp_avg_sq, step, betas=(0.9, 0.999), eps=1e-15):
@@ -118,9 +125,12 @@ class ArenaAdam:
             if p.grad is None or p.grad.data_ptr() != self.grads[name].data_ptr():
                 p.grad = self.grads[name]
 
-    def step(self, grad_scale=1.0, zero_grads=False):
+    def step(self, grad_scale=1.0, zero_grads=False, skip=()):
         """One Adam update of every group with its current `param_groups[i]['lr']`; with zero_grads the gradient arena
-        is cleared in the same pass (step + zero_grad of train.py:422-424 in one launch)."""
+        is cleared in the same pass (step + zero_grad of train.py:422-424 in one launch).
+        `skip`: names of groups that received NO gradient this iteration.  torch.optim.Adam leaves a parameter whose
+        .grad is None untouched (no moment decay, no update); the arena always holds a gradient (zeros), so the caller
+        says which groups to leave out -- they are simply not part of the launch."""
         for name, p in self.params.items():
             if p.grad is None or p.grad.data_ptr() != self.grads[name].data_ptr():
                 raise RuntimeError(f"ArenaAdam: .grad of '{name}' no longer aliases the gradient arena "
@@ -129,8 +139,9 @@ class ArenaAdam:
         a = N.IbgsAdamArgs()
         a.params, a.grads = self.flat_params.data_ptr(), self.flat_grads.data_ptr()
         a.exp_avg, a.exp_avg_sq = self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
-        a.num_groups = len(self.param_groups)
-        for i, g in enumerate(self.param_groups):
+        groups = [g for g in self.param_groups if g["name"] not in skip]
+        a.num_groups = len(groups)
+        for i, g in enumerate(groups):
             off, n = self._ranges[g["name"]]
             a.groups[i].offset, a.groups[i].count, a.groups[i].lr = off, n, float(g["lr"])
         a.beta1, a.beta2, a.eps = self.betas[0], self.betas[1], self.eps

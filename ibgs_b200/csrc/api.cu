@@ -11,12 +11,17 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <atomic>
+#include <mutex>
 
-long long g_launch_count = 0;
+std::atomic<long long> g_launch_count{0};
 
 namespace {
 thread_local char g_err[1024] = "";
-int32_t* g_pinned_count = nullptr;  // pinned host words for the num_rendered read-back (256 bytes)
+// Pinned host words for the num_rendered read-back (256 bytes), ONE SLOT PER HOST THREAD: two threads driving two
+// streams / GPUs concurrently must not see each other's count between the async copy and the host read.
+thread_local int32_t* g_pinned_count = nullptr;
+std::mutex g_prof_mutex;   // the per-stage event timer below is process-global
 }  // namespace
 
 // ---- per-stage event timer -------------------------------------------------------------------------
@@ -47,6 +52,7 @@ void prof_drain() {
 
 void prof_begin(int id, cudaStream_t s) {
   if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   ProfPair p;
   if (!g_prof_free.empty()) {
     p = g_prof_free.back();
@@ -61,7 +67,9 @@ void prof_begin(int id, cudaStream_t s) {
   g_prof_is_open[id] = true;
 }
 void prof_end(int id, cudaStream_t s) {
-  if (!g_prof_on || !g_prof_is_open[id]) return;
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  if (!g_prof_is_open[id]) return;
   cudaEventRecord(g_prof_open[id].b, s);
   g_prof_pending.push_back(g_prof_open[id]);
   g_prof_is_open[id] = false;
@@ -69,11 +77,13 @@ void prof_end(int id, cudaStream_t s) {
 }
 extern "C" void ibgs_profile_enable(int on) { g_prof_on = on != 0; }
 extern "C" void ibgs_profile_reset(void) {
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   prof_drain();
   for (int i = 0; i < PROF_COUNT; i++) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
 }
 extern "C" int ibgs_profile_read(int id, double* ms_total, int64_t* count) {
   if (id < 0 || id >= PROF_COUNT) return IBGS_EINVAL;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   prof_drain();
   if (ms_total) *ms_total = g_prof_ms[id];
   if (count) *count = g_prof_n[id];
@@ -91,7 +101,7 @@ void ibgs_set_error(const char* fmt, ...) {
 
 extern "C" const char* ibgs_last_error(void) { return g_err; }
 extern "C" int ibgs_abi_version(void) { return IBGS_ABI_VERSION; }
-extern "C" int64_t ibgs_launch_count(void) { return g_launch_count; }
+extern "C" int64_t ibgs_launch_count(void) { return g_launch_count.load(); }
 extern "C" void ibgs_release_cached(void) {
   textures_release_all();
   if (g_pinned_count) {

@@ -296,7 +296,8 @@ typedef struct IbgsAdamArgs {
 } IbgsAdamArgs;
 int ibgs_adam_step(const IbgsAdamArgs* args, void* stream);
 
-/* Host-buffer convenience entry points (what a non-torch caller binds; used by bench.py's e2e arm):
+/* Host-buffer convenience entry points (what a non-torch caller binds -- cgo / JNI / ctypes on plain host arrays;
+ * exercised by tests/test_gpu_host_api.py against the device entry points):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages
  * through its own device arena (cudaMallocAsync) and copies results back before returning. */
 int64_t ibgs_forward_h(IbgsForwardArgs* host_args);

@@ -2,7 +2,6 @@
 through its public API (ibgs_b200.diff_plane_rasterization, i.e. through the C ABI), decode its state."""
 import torch
 
-from ibgs_b200 import _native as N
 from ibgs_b200 import synthetic as S
 
 TENSOR_KEYS = ("means3D", "scales", "rotations", "opacities", "shs", "all_map", "bg", "ref_to_src_list",
@@ -93,6 +92,7 @@ def ours_forward_backward(dpr, sc, cot=None, render_geo=True, render_depth_only=
 
 def decode_ours(state):
     """Decodes this implementation's state buffers with ibgs_state_layout (the C ABI's own description)."""
+    from ibgs_b200 import _native as N   # (lazy: bench.py's reference arm imports this module without the library)
     P, H, W, R = state["P"], state["H"], state["W"], state["num_rendered"]
     Npix = H * W
     T = ((W + 15) // 16) * ((H + 15) // 16)

@@ -396,3 +396,35 @@ GAUSSIAN_PARAMS = ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scali
 
 def gaussian_grads(w):
     return {n: getattr(w.gaussians, n).grad for n in GAUSSIAN_PARAMS}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def make_data_parallel(w):
+    """View-sharded data parallelism around the unchanged GaussianModel (ibgs_b200.parallel)."""
+    from ibgs_b200.parallel import GaussianDataParallel
+    w.dp = GaussianDataParallel(w.gaussians, extra_modules=(w.app_model, w.color_net), average=True)
+    return w.dp
+
+
+def dp_train_step(w, cam_indices, views_total, fns=None, sync_stats=False):
+    """One data-parallel optimisation step: this rank runs train_iteration (train.py:269-370) for its views of the batch,
+    gradients accumulate in the flat arenas, ONE all-reduce (+ one small bucket) averages them over the `views_total`
+    views of all ranks, the depth-cache entries the views produced are exchanged, then every rank takes the identical
+    optimizer step (train.py:421-430 with the arena-preserving zero_grad)."""
+    dp = w.dp
+    outs = []
+    for ci in cam_indices:
+        out = train_iteration(w, ci, fns=fns)
+        densification_stats(w, out)
+        outs.append(out)
+    dp.all_reduce_grads(views_total=views_total)
+    dp.sync_depth_cache(w.scene.rendered_depth_list, cam_indices)
+    if sync_stats:
+        dp.sync_densification_stats()
+    w.gaussians.optimizer.step()
+    w.app_model.optimizer.step()
+    if w.opt.use_color_aggregation and w.iteration > w.opt.start_color_aggregation_iter:
+        w.color_opt.step()
+        w.color_iter_count += 1
+    dp.zero_grad()
+    return outs

@@ -357,6 +357,90 @@ __global__ void __launch_bounds__(256 / PPL, PPL == 1 ? 4 : 4) render_forward_ke
         keep = subtile_may_contribute(q0.x, q0.y, q0.z, q0.w, q1.x, q1.z, wx0, wx1, wy0, wy1);
       }
       unsigned m = __ballot_sync(FULL, keep);
+      // render_geo: once EVERY pixel of the warp has T <= 0.5 and its "below" half of the median buffer full (or is
+      // finished), no later pair can enter the buffer (forward.cu:450-463: T only falls, the below part only fills), so
+      // the rest of the list is walked by a copy of the loop without the plane-depth sign test and the ring selects
+      // (the select-based ring + its tests were most of the ALU-pipe load: ALU 52 % vs FMA 25 % in round 1's ncu).
+      bool frozen = false;
+      if (MODE == MODE_GEO) {
+        bool lane_frozen = true;
+#pragma unroll
+        for (int q = 0; q < PPL; q++)
+          lane_frozen = lane_frozen && (done[q] || (!(T[q] > 0.5f) && below_count[q] >= BELOW));
+        frozen = __all_sync(FULL, lane_frozen);
+      }
+      if (frozen) {
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t contributor = (uint32_t)(c0 + b + 1);  // forward.cu:417
+        const float4 g0 = wrec[buf][0][b];
+        const float4 g1 = wrec[buf][1][b];
+        const float dx = g0.x - pixfx;
+#pragma unroll
+        for (int q = 0; q < PPL; q++) {
+          // (nested ifs instead of `continue`: the q loop must unroll completely so that the per-pixel arrays stay
+          // in registers)
+          const float dy = g0.y - pixfy[q];
+          // con_o = (g0.z, g0.w, g1.x, g1.y); forward.cu:421-427
+          const float power = -0.5f * (g0.z * dx * dx + g1.x * dy * dy) - g0.w * dx * dy;
+          const float alpha = min(0.99f, g1.y * exp_power(power));
+          const float test_T = T[q] * (1.0f - alpha);
+          const bool blend = !(done[q] || brk[q]) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+          if (blend && test_T < 0.0001f) done[q] = true;
+          if (blend && !(test_T < 0.0001f)) {
+          const float aT = alpha * T[q];
+
+          const float4 g2 = wrec[buf][2][b];
+          if (MODE != MODE_DEPTH) {
+            C[q][0] += g2.x * aT;
+            C[q][1] += g2.y * aT;
+            C[q][2] += g2.z * aT;
+          }
+          if (MODE != MODE_COLOR) {
+            const float4 g3 = wrec[buf][3][b];
+            // forward.cu:439-442: intersected_depth = -d / (n.ray + eps)
+            if (MODE == MODE_GEO) {
+              normal_accum[q][0] += g3.x * aT;
+              normal_accum[q][1] += g3.y * aT;
+              normal_accum[q][2] += g3.z * aT;
+            } else {  // MODE_DEPTH, forward.cu:466-489 (never reached: the lean walk is render_geo only)
+              const float z_den = g3.x * rayx + g3.y * rayy[q] + g3.z + epsilon;
+              const float intersected_depth = -g2.w / z_den;
+              if (intersected_depth > 0.0f) {
+                if (T[q] > 0.5f) {
+                  // The depth-only ring is only ever consulted for the entry it evicts, so it is kept as a shift
+                  // register (newest entry in slot 0, the evicted one falls out of slot BEFORE-1; empty slots hold
+                  // weight 0) instead of the reference's cyclic pointer: same evicted values in the same order, and
+                  // no dynamically indexed array (which the compiler would place in local memory).
+                  const float old_w = wb[q][BEFORE - 1], old_z = zb[q][BEFORE - 1];
+#pragma unroll
+                  for (int k = BEFORE - 1; k > 0; k--) { zb[q][k] = zb[q][k - 1]; wb[q][k] = wb[q][k - 1]; }
+                  zb[q][0] = intersected_depth;
+                  wb[q][0] = aT;
+                  total_buffer_weight[q] -= old_w;
+                  weighted_depth_sum[q] -= old_w * old_z;
+                  total_buffer_weight[q] += aT;
+                  weighted_depth_sum[q] += aT * intersected_depth;
+                } else if (below_count[q] < BELOW) {
+                  below_count[q]++;
+                  total_buffer_weight[q] += aT;
+                  weighted_depth_sum[q] += aT * intersected_depth;
+                }
+                if (below_count[q] == BELOW) {
+                  // BELOW>0: T<=0.5 from here on, the sums are final -> the pixel is finished.
+                  // BELOW==0: reference semantics = leave this batch, resume at the next.
+                  if (BELOW > 0) done[q] = true; else brk[q] = true;
+                }
+              }
+            }
+          }
+          T[q] = test_T;
+          last_contributor[q] = contributor;
+          }
+        }
+      }
+      } else {
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
@@ -456,6 +540,7 @@ __global__ void __launch_bounds__(256 / PPL, PPL == 1 ? 4 : 4) render_forward_ke
           last_contributor[q] = contributor;
           }
         }
+      }
       }
       all_done = true;
 #pragma unroll

@@ -41,7 +41,7 @@ class IbgsForwardArgs(C.Structure):
         ("out_cam_feat", _fp), ("out_warped_image", _fp), ("out_min_depth_diff", _fp),
         ("out_camera_ray", _fp), ("out_use_first_src_frame", _fp),
         ("alloc", ALLOC_FN), ("alloc_user", C.c_void_p),
-        ("tex_generation_out", C.c_int64),
+        ("tex_generation_out", C.c_int64), ("scratch_capacity_out", C.c_int64),
     ]
 
 

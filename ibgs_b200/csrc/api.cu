@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <atomic>
 #include <mutex>
@@ -22,7 +23,33 @@ thread_local char g_err[1024] = "";
 // streams / GPUs concurrently must not see each other's count between the async copy and the host read.
 thread_local int32_t* g_pinned_count = nullptr;
 std::mutex g_prof_mutex;   // the per-stage event timer below is process-global
+
+// num_rendered of the last forward per (P, W, H, views) shape: sizes the speculative binning scratch of the next one
+struct RHint { int P, W, H, V; int64_t R; };
+std::mutex g_hint_mutex;
+RHint g_hints[8] = {};
+int g_hint_next = 0;
+thread_local cudaEvent_t g_count_event = nullptr;   // marks the end of the num_rendered read-back (one per host thread)
 }  // namespace
+
+int64_t r_hint_get(int P, int W, int H, int V) {
+  std::lock_guard<std::mutex> lock(g_hint_mutex);
+  for (const RHint& h : g_hints)
+    if (h.P == P && h.W == W && h.H == H && h.V == V) return h.R;
+  return 0;
+}
+void r_hint_set(int P, int W, int H, int V, int64_t R) {
+  std::lock_guard<std::mutex> lock(g_hint_mutex);
+  for (RHint& h : g_hints)
+    if (h.P == P && h.W == W && h.H == H && h.V == V) { h.R = R; return; }
+  g_hints[g_hint_next] = RHint{P, W, H, V, R};
+  g_hint_next = (g_hint_next + 1) % 8;
+}
+static int count_event(cudaEvent_t* ev) {
+  if (!g_count_event) CUDA_TRY(cudaEventCreateWithFlags(&g_count_event, cudaEventDisableTiming));
+  *ev = g_count_event;
+  return IBGS_OK;
+}
 
 // ---- per-stage event timer -------------------------------------------------------------------------
 namespace {
@@ -36,7 +63,7 @@ double g_prof_ms[PROF_COUNT] = {0};
 long long g_prof_n[PROF_COUNT] = {0};
 const char* g_prof_names[PROF_COUNT] = {"preprocess", "depth_order_sort", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
                                         "texture_fill", "render_forward", "render_backward", "preprocess_backward",
-                                        "ssim_forward", "ssim_backward"};
+                                        "ssim_forward", "ssim_backward", "tile_sort_histograms"};
 void prof_drain() {
   for (auto& p : g_prof_pending) {
     float ms = 0.f;
@@ -108,6 +135,14 @@ extern "C" void ibgs_release_cached(void) {
     cudaFreeHost(g_pinned_count);
     g_pinned_count = nullptr;
   }
+  if (g_count_event) {
+    cudaEventDestroy(g_count_event);
+    g_count_event = nullptr;
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_hint_mutex);
+    for (RHint& h : g_hints) h = RHint{};
+  }
 }
 
 static int check_view(const IbgsView& v, bool need_src) {
@@ -158,6 +193,7 @@ extern "C" int ibgs_state_layout(int which, size_t count, size_t aux, size_t* of
     ScratchState sc;
     total = carve_scratch(sc, base, count, ibgs_sort_bits((int32_t)(aux ? aux : 1)) - 32);
     offs = {(size_t)sc.tiles_unsorted, (size_t)sc.tiles_sorted, (size_t)sc.vals_unsorted, (size_t)sc.sort_temp};
+    // (count = the CAPACITY the scratch was carved for: IbgsForwardArgs.scratch_capacity_out)
   } else {
     ibgs_set_error("unknown buffer id %d", which);
     return IBGS_EINVAL;
@@ -171,6 +207,7 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
   cudaStream_t s = (cudaStream_t)stream_v;
   if (!a) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
   a->tex_generation_out = 0;
+  a->scratch_capacity_out = 0;
   const int P = a->P;
   if (P < 0) { ibgs_set_error("P must be >= 0"); return IBGS_EINVAL; }
   if (P == 0) return 0;  // rasterize_points.cu:101-102: outputs stay zero, rendered = 0
@@ -226,21 +263,45 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
   }
 
   if (!g_pinned_count) CUDA_TRY(cudaHostAlloc((void**)&g_pinned_count, 256, cudaHostAllocDefault));
+  cudaEvent_t ev = nullptr;
+  rc = count_event(&ev);
+  if (rc != IBGS_OK) return rc;
 
-  // We do not know R yet: the first scratch request holds the P-sized depth-order state, the second one (once R
-  // is known) the R-sized binning temporaries.  Both stay alive until the forward's last launch is enqueued.
+  // We do not know R yet: the first scratch request holds the P-sized depth-order state, the second one the R-sized
+  // binning temporaries.  Both stay alive until the forward's last launch is enqueued.
   OrderState ord;
   const size_t order_bytes = carve_order(ord, nullptr, (size_t)P);
   char* order_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, order_bytes);
   if (!order_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
   carve_order(ord, order_base, (size_t)P);
 
-  rc = launch_preprocess(*a, g, ord.iota, focal_x, focal_y, grid, s);
+  rc = launch_preprocess(*a, g, focal_x, focal_y, grid, s);
   if (rc != IBGS_OK) return rc;
   rc = run_depth_order(g, ord, (size_t)P, s);
   if (rc != IBGS_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(g_pinned_count, ord.offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaStreamSynchronize(s));
+  CUDA_TRY(cudaEventRecord(ev, s));
+
+  // Speculative binning: emission and the front half of the tile sort are queued NOW, into a scratch sized from the
+  // instance count this (P, W, H) shape produced last time, so the GPU is busy while the host waits for the 4 bytes.
+  // The kernels read R on the device and never touch memory beyond the capacity; if R turns out larger (first call,
+  // scene change) they are simply queued again with the exact size -- the reference's order of events.
+  const int tile_bits = ibgs_sort_bits((int32_t)T) - 32;
+  ScratchState sc;
+  size_t cap = 0;
+  static const bool no_spec = getenv("IBGS_NO_SPECULATION") != nullptr;   // (A/B switch for profiles/NOTES.md)
+  const int64_t hint = no_spec ? 0 : r_hint_get(P, W, H, 1);
+  if (hint > 0) {
+    cap = (size_t)(hint + hint / 8 + 4096);
+    if (cap > 0x7fffffffull) cap = 0x7fffffffull;
+    const size_t bytes = carve_scratch(sc, nullptr, cap, tile_bits);
+    char* base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, bytes);
+    if (!base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+    carve_scratch(sc, base, cap, tile_bits);
+    rc = run_binning_begin(P, a->radii, v.debug, 1, g, ord, sc, cap, grid, s);
+    if (rc != IBGS_OK) return rc;
+  }
+  CUDA_TRY(cudaEventSynchronize(ev));   // the copy only -- NOT the kernels queued behind it
   const uint32_t R_u = *(volatile uint32_t*)g_pinned_count;
   if (R_u > 0x7fffffffu) {
     // the reference stores this in an int (rasterizer_impl.cu:429) and would overflow
@@ -248,18 +309,24 @@ extern "C" int64_t ibgs_forward(IbgsForwardArgs* a, void* stream_v) {
     return IBGS_ELIMIT;
   }
   const int64_t R = (int64_t)R_u;
+  r_hint_set(P, W, H, 1, R);
+  if ((size_t)R > cap || hint <= 0) {
+    cap = (size_t)R;
+    const size_t bytes = carve_scratch(sc, nullptr, cap, tile_bits);
+    char* base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, bytes);
+    if (!base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
+    carve_scratch(sc, base, cap, tile_bits);
+    rc = run_binning_begin(P, a->radii, v.debug, 1, g, ord, sc, cap, grid, s);
+    if (rc != IBGS_OK) return rc;
+  }
+  a->scratch_capacity_out = (int64_t)cap;
 
   BinningState b;
   size_t bin_bytes = carve_binning(b, nullptr, (size_t)R);
   char* bin_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_BINNING, bin_bytes);
   if (!bin_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
   carve_binning(b, bin_base, (size_t)R);
-
-  ScratchState sc;
-  size_t scratch_bytes = carve_scratch(sc, nullptr, (size_t)R, ibgs_sort_bits((int32_t)T) - 32);
-  char* scratch_base = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, scratch_bytes);
-  if (!scratch_base) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
-  rc = run_binning(*a, g, ord, im, scratch_base, scratch_bytes, b, R, grid, s);
+  rc = run_binning_finish(P, v.debug, 1, ord, sc, im.ranges, b, grid, s);
   if (rc != IBGS_OK) return rc;
 
   rc = launch_render_forward(*a, g, im, b, tex, focal_x, focal_y, grid, R, s);
@@ -339,7 +406,7 @@ extern "C" int64_t ibgs_forward_depth_batch(IbgsDepthBatchArgs* a, void* stream_
   if (!g_pinned_count) CUDA_TRY(cudaHostAlloc((void**)&g_pinned_count, 256, cudaHostAllocDefault));
   CUDA_TRY(cudaMemsetAsync(counts, 0, counts_bytes, s));
   COUNT_LAUNCH();
-  int rc = launch_preprocess_depth_batch(*a, g, radii, ord.iota, counts, focal_x, focal_y, grid, s);
+  int rc = launch_preprocess_depth_batch(*a, g, radii, counts, focal_x, focal_y, grid, s);
   if (rc != IBGS_OK) return rc;
   rc = run_depth_order(g, ord, items, s);
   if (rc != IBGS_OK) return rc;
@@ -364,7 +431,10 @@ extern "C" int64_t ibgs_forward_depth_batch(IbgsDepthBatchArgs* a, void* stream_
   char* base2 = (char*)a->alloc(a->alloc_user, IBGS_BUF_SCRATCH, bin_bytes + scratch_bytes);
   if (!base2) { ibgs_set_error("allocator returned NULL"); return IBGS_EALLOC; }
   carve_binning(b, base2, (size_t)R);
-  rc = run_binning_items((int)items, radii, a->debug, V, g, ord, ranges, base2 + bin_bytes, scratch_bytes, b, R, grid, s);
+  carve_scratch(sc, base2 + bin_bytes, (size_t)R, ibgs_sort_bits((int32_t)(T * V)) - 32);
+  rc = run_binning_begin((int)items, radii, a->debug, V, g, ord, sc, (size_t)R, grid, s);
+  if (rc != IBGS_OK) return rc;
+  rc = run_binning_finish((int)items, a->debug, V, ord, sc, ranges, b, grid, s);
   if (rc != IBGS_OK) return rc;
   rc = launch_render_depth_batch(*a, g, ranges, b, focal_x, focal_y, grid, R, s);
   if (rc != IBGS_OK) return rc;

@@ -6,28 +6,24 @@
 // `point_list` ordered by tile, then by depth bits, ties by Gaussian id (stable sort, Gaussian-major emission)
 // -- and the tile ranges are what every later stage consumes; they are reproduced here bit for bit.
 //
-// How (this project's own decomposition; the radix sorts and the scan are CCCL/CUB device primitives, library
-// code like in the reference).  A 64-bit LSD sort of all R instances is 6 passes over 24-byte pairs at R = 15 M.
-// The depth half of the key is a property of the GAUSSIAN, not of the instance, so it is sorted once per
-// Gaussian instead of once per instance:
-//   1. stable sort of the P Gaussians by depth bits (32-bit keys, P << R items); culled Gaussians carry the key
-//      0xFFFFFFFF and land behind every visible one;
-//   2. inclusive scan of tiles_touched in that order -> write offsets;
-//   3. emission in depth order: instance = (tile id u32, Gaussian id u32), warp-cooperative for big rectangles;
-//   4. stable sort of the R instances by tile id only: ceil(msb(T)/8) = 2 passes over 8-byte pairs;
-//   5. tile ranges from the sorted tile ids.
+// How (this project's own decomposition, on this project's own sort / scan primitives, sort.cu -- no library code).
+// A 64-bit LSD sort of all R instances is 6 passes over 24-byte pairs at R = 15 M.  The depth half of the key is a
+// property of the GAUSSIAN, not of the instance, so it is sorted once per Gaussian instead of once per instance:
+//   1. stable sort of the P Gaussians by depth bits (32-bit keys, P << R items, three 11/11/10-bit multisplit passes);
+//      culled Gaussians carry the key 0xFFFFFFFF and land behind every visible one;
+//   2. inclusive scan of tiles_touched in that order -> write offsets; offsets[P-1] = num_rendered;
+//   3. emission in depth order: instance = (tile id u16/u32, Gaussian id u32), warp-cooperative for big rectangles;
+//   4. stable sort of the R instances by tile id only: ONE multisplit pass with 2^13 bins at 1080p (two above 8192
+//      tiles or in batched depth renders);
+//   5. tile ranges: a by-product of the sort's bin totals (one pass) or identify_tile_ranges_kernel (two passes).
 // Stability of (4) keeps each tile's instances in emission order = ascending depth bits, ties in ascending
 // Gaussian id (stability of (1)) -- exactly the reference's order.  The reference's sorted 64-bit keys are
 // (tile id << 32 | depth bits of point_list[i]); tests rebuild them from this state and compare bit-exactly.
+// Steps 3-4 are queued BEFORE the host knows num_rendered (run_binning_begin: the kernels read it on the device and are
+// bounded by the scratch capacity), so the GPU keeps working while the 4-byte read-back is in flight (api.cu).
 #include "common.cuh"
-#include <cub/cub.cuh>
 
 namespace {
-
-struct GatherTiles {
-  const uint32_t* tiles;
-  __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& g) const { return tiles[g]; }
-};
 
 // One thread per position in depth order; one warp per 32 positions; rectangles with >= 8 tiles are written
 // cooperatively by the whole warp.  Tile order inside a rectangle is row-major like rasterizer_impl.cu:215-226
@@ -42,7 +38,8 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
                                                              const int* __restrict__ radii,
                                                              TileT* __restrict__ tile_ids,
                                                              uint32_t* __restrict__ vals, dim3 grid,
-                                                             uint32_t items_per_view, uint32_t tiles_per_view) {
+                                                             uint32_t items_per_view, uint32_t tiles_per_view,
+                                                             uint32_t cap) {
   const int pos = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
   uint32_t gid = 0, n = 0, off = 0, tbase = 0;
@@ -53,6 +50,11 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
   }
   if (n > 0) {
     off = (pos == 0) ? 0 : offsets[pos - 1];
+    // speculative launch: the scratch holds `cap` instances.  If num_rendered turns out larger the host re-runs the
+    // emission into a bigger scratch; until then nothing may be written past the end
+    if ((uint64_t)off + n > cap) n = 0;
+  }
+  if (n > 0) {
     const float4 q0 = rec[4 * (size_t)gid];
     getRect(make_float2(q0.x, q0.y), radii[gid], rmin, rmax, grid);
     if (BATCH) tbase = (gid / items_per_view) * tiles_per_view;
@@ -92,8 +94,10 @@ __global__ void __launch_bounds__(256) emit_instances_kernel(int P, const uint32
 // takes the 16 bytes of ids starting at a 16-byte boundary (8 uint16 or 4 uint32: one vector load) plus the id before
 // them; the reference's one-thread-per-instance form is launch- and tail-bound at 15 M instances.
 template <typename TileT>
-__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(int L, const TileT* __restrict__ tile_ids, uint2* ranges) {
+__global__ void __launch_bounds__(256) identify_tile_ranges_kernel(const uint32_t* __restrict__ n_dev, uint32_t n_cap,
+                                                                   const TileT* __restrict__ tile_ids, uint2* ranges) {
   constexpr int PER = 16 / sizeof(TileT);
+  const int L = (int)min(*n_dev, n_cap);
   const int base = (blockIdx.x * blockDim.x + threadIdx.x) * PER;
   if (base >= L) return;
   TileT ids[PER];
@@ -142,19 +146,14 @@ extern "C" int ibgs_sort_bits(int32_t num_tiles) { return 32 + (int)getHigherMsb
 
 size_t carve_order(OrderState& o, char* base, size_t P) {
   size_t off = 0;
-  carve(off, o.iota, base, P);
   carve(off, o.keys_sorted, base, P);
   carve(off, o.order, base, P);
   carve(off, o.offsets, base, P);
-  size_t sort_bytes = 0, scan_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)P, 0, 32);
-  cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t*> it((const uint32_t*)nullptr, GatherTiles{nullptr});
-  cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, it, (uint32_t*)nullptr, (int)P);
-  o.temp_bytes = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+  o.plan = sort_plan(P, 32, 4);
   off = align_up(off, 256);
   o.temp = base + off;
-  off += o.temp_bytes;
+  o.scan_off = o.plan.bytes;
+  off += o.plan.bytes + scan_temp_bytes(P);
   return align_up(off, 256);
 }
 
@@ -162,70 +161,47 @@ size_t carve_order(OrderState& o, char* base, size_t P) {
 int run_depth_order(const GeomState& g, const OrderState& o, size_t P, cudaStream_t s) {
   {
     ProfScope prof(PROF_GSORT, s);
-    size_t tb = o.temp_bytes;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(o.temp, tb, reinterpret_cast<const uint32_t*>(g.depths), o.keys_sorted,
-                                             o.iota, o.order, (int)P, 0, 32, s));
-    g_launch_count += 5;
+    // values = Gaussian ids = positions in the input: no identity-permutation array
+    int rc = sort_pairs(o.plan, g.depths, nullptr, o.keys_sorted, o.order, nullptr, o.temp, s, 0);
+    if (rc != IBGS_OK) return rc;
   }
   {
     ProfScope prof(PROF_SCAN, s);
-    size_t tb = o.temp_bytes;
-    cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t*> it(o.order, GatherTiles{g.tiles_touched});
-    CUDA_TRY(cub::DeviceScan::InclusiveSum(o.temp, tb, it, o.offsets, (int)P, s));
-    g_launch_count += 2;
+    int rc = scan_gather_inclusive(P, o.order, g.tiles_touched, o.offsets, o.temp + o.scan_off, s, 0);
+    if (rc != IBGS_OK) return rc;
   }
   return IBGS_OK;
 }
 
 // Tile ids are stored as uint16 whenever the image has at most 65536 tiles (every resolution up to 4096x4096):
-// the tile sort then moves 6 instead of 8 bytes per instance and pass.  The arrays are carved for the wider type.
-size_t carve_scratch(ScratchState& sc, char* base, size_t R, int tile_bits) {
+// the tile sort then moves 6 instead of 8 bytes per instance.  The arrays are carved for the wider type.
+size_t carve_scratch(ScratchState& sc, char* base, size_t cap, int tile_bits) {
   size_t off = 0;
-  carve(off, sc.tiles_unsorted, base, R);
-  carve(off, sc.tiles_sorted, base, R);
-  carve(off, sc.vals_unsorted, base, R);
-  size_t bytes = 0, bytes16 = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)R, 0, tile_bits);
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes16, (uint16_t*)nullptr, (uint16_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)R, 0, tile_bits < 16 ? tile_bits : 16);
-  if (bytes16 > bytes) bytes = bytes16;
-  sc.sort_temp_bytes = bytes;
+  carve(off, sc.tiles_unsorted, base, cap);
+  carve(off, sc.tiles_sorted, base, cap);
+  carve(off, sc.vals_unsorted, base, cap);
+  sc.plan = sort_plan(cap, tile_bits, tile_bits <= 16 ? 2 : 4);
   off = align_up(off, 256);
   sc.sort_temp = base + off;
-  off += bytes;
+  off += sc.plan.bytes;
   return align_up(off, 256);
-}
-
-// steps 3-5
-int run_binning(const IbgsForwardArgs& a, const GeomState& g, const OrderState& o, const ImageState& im,
-                char* scratch_base, size_t scratch_bytes, BinningState& b, int64_t R, dim3 grid, cudaStream_t s) {
-  return run_binning_items(a.P, a.radii, a.view.debug, 1, g, o, im.ranges, scratch_base, scratch_bytes, b, R, grid, s);
 }
 
 // P items; with views > 1 they are (view, Gaussian) pairs (item id = view * P/views + Gaussian) and ranges has
 // views * tiles entries
-int run_binning_items(int P, const int* radii, int debug, int views, const GeomState& g, const OrderState& o,
-                      uint2* ranges, char* scratch_base, size_t scratch_bytes, BinningState& b, int64_t R, dim3 grid,
-                      cudaStream_t s) {
+int run_binning_begin(int P, const int* radii, int debug, int views, const GeomState& g, const OrderState& o,
+                      ScratchState& sc, size_t cap, dim3 grid, cudaStream_t s) {
   const uint32_t tiles_per_view = grid.x * grid.y;
   const uint32_t items_per_view = (uint32_t)(P / views);
-  const int tile_bits = ibgs_sort_bits((int32_t)(tiles_per_view * views)) - 32;
-  ScratchState sc;
-  size_t need = carve_scratch(sc, scratch_base, (size_t)R, tile_bits);
-  if (need > scratch_bytes) {
-    ibgs_set_error("scratch too small: %zu < %zu", scratch_bytes, need);
-    return IBGS_EINVAL;
-  }
-  const bool narrow = tile_bits <= 16;
+  const bool narrow = sc.plan.key_bytes == 2;
   uint16_t* t16_unsorted = reinterpret_cast<uint16_t*>(sc.tiles_unsorted);
-  uint16_t* t16_sorted = reinterpret_cast<uint16_t*>(sc.tiles_sorted);
   {
     ProfScope prof(PROF_DUPLICATE, s);
     const int nb = (P + 255) / 256;
 #define EMIT(T, BATCH, dst)                                                                                          \
   emit_instances_kernel<T, BATCH><<<nb, 256, 0, s>>>(P, o.order, g.tiles_touched, o.offsets, g.rec, radii, dst,      \
-                                                     sc.vals_unsorted, grid, items_per_view, tiles_per_view)
+                                                     sc.vals_unsorted, grid, items_per_view, tiles_per_view,         \
+                                                     (uint32_t)cap)
     if (views > 1) {
       if (narrow) EMIT(uint16_t, true, t16_unsorted); else EMIT(uint32_t, true, sc.tiles_unsorted);
     } else {
@@ -234,24 +210,41 @@ int run_binning_items(int P, const int* radii, int debug, int views, const GeomS
 #undef EMIT
     KERNEL_CHECK(debug, s);
   }
-  if (R > 0) {
-    ProfScope prof(PROF_SORT, s);
-    if (narrow)
-      CUDA_TRY(cub::DeviceRadixSort::SortPairs(sc.sort_temp, sc.sort_temp_bytes, t16_unsorted, t16_sorted,
-                                               sc.vals_unsorted, b.point_list, (int)R, 0, tile_bits, s));
-    else
-      CUDA_TRY(cub::DeviceRadixSort::SortPairs(sc.sort_temp, sc.sort_temp_bytes, sc.tiles_unsorted, sc.tiles_sorted,
-                                               sc.vals_unsorted, b.point_list, (int)R, 0, tile_bits, s));
-    g_launch_count += (tile_bits + 7) / 8 + 1;
+  if (cap > 0) {
+    ProfScope prof(PROF_SORT_FRONT, s);
+    // the output pointers of the last scatter are not needed yet (single pass) / are the scratch's own (two passes)
+    int rc = sort_pairs_begin(sc.plan, sc.tiles_unsorted, sc.vals_unsorted, sc.tiles_sorted, nullptr, o.offsets + (P - 1),
+                              sc.sort_temp, s, debug);
+    if (rc != IBGS_OK) return rc;
   }
-  {
+  return IBGS_OK;
+}
+
+int run_binning_finish(int P, int debug, int views, const OrderState& o, ScratchState& sc, uint2* ranges, BinningState& b,
+                       dim3 grid, cudaStream_t s) {
+  const uint32_t tiles = grid.x * grid.y * (uint32_t)views;
+  const uint32_t* n_dev = o.offsets + (P - 1);
+  const bool one_pass = sc.plan.npass == 1;
+  if (sc.plan.n_cap > 0) {
+    ProfScope prof(PROF_SORT, s);
+    // one pass: the sorted tile ids are not written at all (every store of the scatter is a separate 32-byte sector
+    // request -- the pass is bound by their rate -- and the ranges already say which tile a list position belongs to)
+    int rc = sort_pairs_finish(sc.plan, sc.tiles_unsorted, sc.vals_unsorted, one_pass ? nullptr : (void*)sc.tiles_sorted,
+                               b.point_list, n_dev, sc.sort_temp, one_pass ? ranges : nullptr, tiles, s, debug);
+    if (rc != IBGS_OK) return rc;
+  }
+  if (!one_pass || sc.plan.n_cap == 0) {
     ProfScope prof(PROF_RANGES, s);
-    CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)tiles_per_view * views * sizeof(uint2), s));
-    if (R > 0) {
-      if (narrow)
-        identify_tile_ranges_kernel<uint16_t><<<(int)((R + 256 * 8 - 1) / (256 * 8)), 256, 0, s>>>((int)R, t16_sorted, ranges);
+    CUDA_TRY(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), s));
+    COUNT_LAUNCH();
+    if (sc.plan.n_cap > 0) {
+      const size_t R = sc.plan.n_cap;   // grid sized for the capacity, the kernel stops at *n_dev
+      if (sc.plan.key_bytes == 2)
+        identify_tile_ranges_kernel<uint16_t><<<(int)((R + 256 * 8 - 1) / (256 * 8)), 256, 0, s>>>(
+            n_dev, (uint32_t)R, reinterpret_cast<const uint16_t*>(sc.tiles_sorted), ranges);
       else
-        identify_tile_ranges_kernel<uint32_t><<<(int)((R + 256 * 4 - 1) / (256 * 4)), 256, 0, s>>>((int)R, sc.tiles_sorted, ranges);
+        identify_tile_ranges_kernel<uint32_t><<<(int)((R + 256 * 4 - 1) / (256 * 4)), 256, 0, s>>>(
+            n_dev, (uint32_t)R, sc.tiles_sorted, ranges);
       KERNEL_CHECK(debug, s);
     }
   }

@@ -10,7 +10,6 @@
 // order-preserving integers; the Morton-sorted points are gathered once into a float4 array so the
 // neighbour scan reads contiguous memory instead of points[indices[i]]; 256-thread CTAs.
 #include "common.cuh"
-#include <cub/cub.cuh>
 #include <cfloat>
 
 #define BOX_SIZE 1024
@@ -190,8 +189,8 @@ struct KnnScratch {
   uint32_t* idx_sorted;
   float4* sorted;
   MinMax* boxes;
-  void* sort_temp;
-  size_t sort_temp_bytes;
+  char* sort_temp;
+  SortPlan plan;
 };
 
 size_t carve_knn(KnnScratch& k, char* base, size_t P) {
@@ -203,13 +202,10 @@ size_t carve_knn(KnnScratch& k, char* base, size_t P) {
   carve(off, k.idx_sorted, base, P);
   carve(off, k.sorted, base, P);
   carve(off, k.boxes, base, (P + BOX_SIZE - 1) / BOX_SIZE);
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)P, 0, 30);
-  k.sort_temp_bytes = bytes;
+  k.plan = sort_plan(P, 30, 4);   // Morton codes occupy 30 bits: three 10-bit multisplit passes (sort.cu)
   off = align_up(off, 256);
   k.sort_temp = base + off;
-  off += bytes;
+  off += k.plan.bytes;
   return align_up(off, 256);
 }
 
@@ -237,9 +233,10 @@ extern "C" int ibgs_dist2(int32_t P, const float* points, float* mean_dists, voi
   morton_kernel<<<blocks, 256, 0, s>>>(P, points, k.bounds, k.codes, k.idx);
   KERNEL_CHECK(0, s);
   // codes occupy 30 bits, so sorting bits [0,30) is identical to the reference's full 32-bit sort (:210-213)
-  CUDA_TRY(cub::DeviceRadixSort::SortPairs(k.sort_temp, k.sort_temp_bytes, k.codes, k.codes_sorted, k.idx,
-                                           k.idx_sorted, P, 0, 30, s));
-  g_launch_count += 5;
+  {
+    int rc = sort_pairs(k.plan, k.codes, k.idx, k.codes_sorted, k.idx_sorted, nullptr, k.sort_temp, s, 0);
+    if (rc != IBGS_OK) return rc;
+  }
   gather_kernel<<<blocks, 256, 0, s>>>(P, points, k.idx_sorted, k.sorted);
   KERNEL_CHECK(0, s);
   const int nb = (P + BOX_SIZE - 1) / BOX_SIZE;

@@ -37,7 +37,6 @@ struct PreArgs {
   float* depths;
   uint32_t* tiles_touched;
   uint8_t* clamped;
-  uint32_t* iota;
   dim3 grid;
   int prefiltered;
   int render_depth_only;
@@ -155,7 +154,6 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreArgs a) {
   a.radii[idx] = 0;
   a.tiles_touched[idx] = 0;
   // binning.cu sorts the Gaussians by the bit pattern of depths[]: culled ones get the largest key
-  a.iota[idx] = idx;
   reinterpret_cast<uint32_t*>(a.depths)[idx] = 0xFFFFFFFFu;
 
   // in_frustum, auxiliary.h:143-168
@@ -262,7 +260,6 @@ struct PreBatchArgs {
   float4* rec;
   float* depths;
   uint32_t* tiles_touched;
-  uint32_t* iota;
   unsigned long long* counts;
   dim3 grid;
   int prefiltered;
@@ -351,7 +348,6 @@ __global__ void __launch_bounds__(256) preprocess_depth_batch_kernel(const PreBa
     if (valid) {
       a.radii[o] = radius_out;
       a.tiles_touched[o] = tiles;
-      a.iota[o] = (uint32_t)o;
       reinterpret_cast<uint32_t*>(a.depths)[o] = depth_bits;
     }
     if (a.counts != nullptr) {
@@ -372,7 +368,7 @@ __global__ void mark_visible_kernel(int P, const float* means3D, const float* vi
 
 }  // namespace
 
-int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, uint32_t* iota, float focal_x, float focal_y,
+int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, float focal_x, float focal_y,
                       dim3 grid, cudaStream_t s) {
   PreArgs a;
   a.P = f.P;
@@ -402,7 +398,6 @@ int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, uint32_t* io
   a.depths = g.depths;
   a.tiles_touched = g.tiles_touched;
   a.clamped = g.clamped;
-  a.iota = iota;
   a.grid = grid;
   a.prefiltered = f.view.prefiltered;
   a.render_depth_only = f.view.render_depth_only;
@@ -412,7 +407,7 @@ int launch_preprocess(const IbgsForwardArgs& f, const GeomState& g, uint32_t* io
   return IBGS_OK;
 }
 
-int launch_preprocess_depth_batch(const IbgsDepthBatchArgs& f, const GeomState& g, int* radii, uint32_t* iota,
+int launch_preprocess_depth_batch(const IbgsDepthBatchArgs& f, const GeomState& g, int* radii,
                                   unsigned long long* counts, float focal_x, float focal_y, dim3 grid,
                                   cudaStream_t s) {
   PreBatchArgs a;
@@ -440,7 +435,6 @@ int launch_preprocess_depth_batch(const IbgsDepthBatchArgs& f, const GeomState& 
   a.rec = g.rec;
   a.depths = g.depths;
   a.tiles_touched = g.tiles_touched;
-  a.iota = iota;
   a.counts = counts;
   a.grid = grid;
   a.prefiltered = f.prefiltered;

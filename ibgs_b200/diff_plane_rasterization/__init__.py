@@ -235,7 +235,8 @@ class _RasterizeGaussians(torch.autograd.Function):
             LAST_STATE.clear()
             LAST_STATE.update(geom=geomBuffer, binning=binningBuffer, image=imgBuffer,
                               scratch=alloc.scratch[-1] if alloc.scratch else empty,
-                              num_rendered=num_rendered, P=P, H=H, W=W)
+                              num_rendered=num_rendered, P=P, H=H, W=W,
+                              scratch_capacity=int(a.scratch_capacity_out))
         a.alloc = N.ALLOC_FN()
         alloc.release()
 

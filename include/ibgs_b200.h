@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IBGS_ABI_VERSION 3
+#define IBGS_ABI_VERSION 4
 
 /* Compile-time constants of the reference (cuda_rasterizer/config.h:15-19, auxiliary.h:21-23). */
 #define IBGS_NUM_CHANNELS 3
@@ -101,6 +101,8 @@ typedef struct IbgsForwardArgs {
   ibgs_alloc_fn alloc;
   void* alloc_user;
   int64_t tex_generation_out;  /* written by the library: id of the texture fill, see backward */
+  int64_t scratch_capacity_out; /* written by the library: instance capacity the LAST scratch request was carved for
+                                 * (>= num_rendered; pass it as `count` to ibgs_state_layout(IBGS_BUF_SCRATCH, ...)) */
 } IbgsForwardArgs;
 
 /* returns num_rendered (tile instances R) */

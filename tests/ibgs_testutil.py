@@ -117,13 +117,21 @@ def decode_ours(state):
                valid_w=view(im, io[6], 5 * Npix, torch.float32).view(5, Npix),
                ranges=view(im, io[7], 2 * T, torch.int32).view(T, 2))
     out["point_list"] = view(b, 0, R, torch.int32)
-    so, _ = N.state_layout(N.IBGS_BUF_SCRATCH, R, T)
-    if N.lib.ibgs_sort_bits(T) - 32 <= 16:   # tile ids are stored as uint16 up to 65536 tiles (binning.cu)
+    so, _ = N.state_layout(N.IBGS_BUF_SCRATCH, state.get("scratch_capacity", R) or R, T)
+    tile_bits = N.lib.ibgs_sort_bits(T) - 32
+    if tile_bits <= 16:   # tile ids are stored as uint16 up to 65536 tiles (binning.cu)
         out["tiles_unsorted"] = view(sc, so[0], R, torch.int16).int() & 0xFFFF
         out["tiles_sorted"] = view(sc, so[1], R, torch.int16).int() & 0xFFFF
     else:
         out["tiles_unsorted"] = view(sc, so[0], R, torch.int32)
         out["tiles_sorted"] = view(sc, so[1], R, torch.int32)
+    if tile_bits <= 8:
+        # single-pass tile sort (tiny images): the sorted tile ids are not stored; the ranges (compared with the reference's on their
+        # own) say which tile every list position belongs to
+        rg = out["ranges"].long()
+        counts = rg[:, 1] - rg[:, 0]
+        assert int(counts.sum()) == R and bool((rg[1:, 0][counts[1:] > 0] >= rg[:-1, 0].cummax(0).values[counts[1:] > 0]).all())
+        out["tiles_sorted"] = torch.repeat_interleave(torch.arange(T, device=rg.device, dtype=torch.int32), counts)
     out["point_list_unsorted"] = view(sc, so[2], R, torch.int32)
     # the reference's 64-bit sort keys (tile id << 32 | depth bits, rasterizer_impl.cu:219-223) rebuilt from
     # this implementation's state: tile id of every instance + depth of the Gaussian it points to

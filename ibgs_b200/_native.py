@@ -114,6 +114,7 @@ EXPORTS = [
     "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
     "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
     "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward", "ibgs_adam_step", "ibgs_set_backward_variant", "ibgs_set_forward_variant",
+    "ibgs_sort_temp_bytes", "ibgs_sort_pairs", "ibgs_scan_temp_bytes", "ibgs_scan_gather",
 ]
 
 
@@ -166,6 +167,14 @@ def _load():
         fn.argtypes = [C.c_int]
     lib.ibgs_adam_step.restype = C.c_int
     lib.ibgs_adam_step.argtypes = [C.POINTER(IbgsAdamArgs), C.c_void_p]
+    lib.ibgs_sort_temp_bytes.restype = C.c_size_t
+    lib.ibgs_sort_temp_bytes.argtypes = [C.c_int64, C.c_int, C.c_int]
+    lib.ibgs_sort_pairs.restype = C.c_int
+    lib.ibgs_sort_pairs.argtypes = [_fp, _fp, _fp, _fp, C.c_int64, C.c_int, C.c_int, _fp, C.c_size_t, C.c_void_p]
+    lib.ibgs_scan_temp_bytes.restype = C.c_size_t
+    lib.ibgs_scan_temp_bytes.argtypes = [C.c_int64]
+    lib.ibgs_scan_gather.restype = C.c_int
+    lib.ibgs_scan_gather.argtypes = [C.c_int64, _fp, _fp, _fp, _fp, C.c_size_t, C.c_void_p]
     lib.ibgs_forward_depth_batch.restype = C.c_int64
     lib.ibgs_forward_depth_batch.argtypes = [C.POINTER(IbgsDepthBatchArgs), C.c_void_p]
     return lib

@@ -466,3 +466,29 @@ int scan_gather_inclusive(size_t n, const uint32_t* idx, const uint32_t* src, ui
   KERNEL_CHECK(debug, s);
   return IBGS_OK;
 }
+
+// ---- C ABI (include/ibgs_b200.h) ---------------------------------------------------------------------------------------
+extern "C" size_t ibgs_sort_temp_bytes(int64_t n, int key_bits, int key_bytes) {
+  if (n < 0 || (key_bytes != 2 && key_bytes != 4)) return 0;
+  return sort_plan((size_t)n, key_bits, key_bytes).bytes;
+}
+extern "C" int ibgs_sort_pairs(const void* keys_in, const uint32_t* vals_in, void* keys_out, uint32_t* vals_out, int64_t n,
+                               int key_bits, int key_bytes, void* temp, size_t temp_bytes, void* stream) {
+  if (n < 0 || n > 0x7fffffffLL) { ibgs_set_error("n must be in [0, 2^31), got %lld", (long long)n); return IBGS_EINVAL; }
+  if (key_bytes != 2 && key_bytes != 4) { ibgs_set_error("key_bytes must be 2 or 4, got %d", key_bytes); return IBGS_EINVAL; }
+  if (key_bits < 1 || key_bits > 8 * key_bytes) { ibgs_set_error("key_bits must be in [1,%d], got %d", 8 * key_bytes, key_bits); return IBGS_EINVAL; }
+  if (n == 0) return IBGS_OK;
+  if (!keys_in || !keys_out || !vals_out || !temp) { ibgs_set_error("null pointer"); return IBGS_EINVAL; }
+  const SortPlan p = sort_plan((size_t)n, key_bits, key_bytes);
+  if (temp_bytes < p.bytes) { ibgs_set_error("temp too small: %zu < %zu", temp_bytes, p.bytes); return IBGS_EINVAL; }
+  return sort_pairs(p, keys_in, vals_in, keys_out, vals_out, nullptr, (char*)temp, (cudaStream_t)stream, 0);
+}
+extern "C" size_t ibgs_scan_temp_bytes(int64_t n) { return n < 0 ? 0 : scan_temp_bytes((size_t)n); }
+extern "C" int ibgs_scan_gather(int64_t n, const uint32_t* idx, const uint32_t* src, uint32_t* out, void* temp,
+                                size_t temp_bytes, void* stream) {
+  if (n < 0 || n > 0x7fffffffLL) { ibgs_set_error("n must be in [0, 2^31), got %lld", (long long)n); return IBGS_EINVAL; }
+  if (n == 0) return IBGS_OK;
+  if (!idx || !src || !out || !temp) { ibgs_set_error("null pointer"); return IBGS_EINVAL; }
+  if (temp_bytes < scan_temp_bytes((size_t)n)) { ibgs_set_error("temp too small"); return IBGS_EINVAL; }
+  return scan_gather_inclusive((size_t)n, idx, src, out, temp, (cudaStream_t)stream, 0);
+}

@@ -305,6 +305,19 @@ int ibgs_adam_step(const IbgsAdamArgs* args, void* stream);
 int64_t ibgs_forward_h(IbgsForwardArgs* host_args);
 int ibgs_dist2_h(int32_t P, const float* points_host, float* mean_dists_host);
 
+/* The binning stage's own device primitives (csrc/sort.cu; they replace cub::DeviceRadixSort::SortPairs /
+ * cub::DeviceScan::InclusiveSum of rasterizer_impl.cu:426,452-457 and simple_knn.cu:210-213), exported so that they can
+ * be tested on their own.  ibgs_sort_pairs: stable ascending sort of n (key, value) pairs on the low `key_bits` bits of
+ * uint16 (key_bytes 2) or uint32 (4) keys; values uint32, vals_in NULL = the item's index.  ibgs_scan_gather:
+ * out[i] = sum_{j<=i} src[idx[j]].  All pointers are device pointers; `temp` must hold ibgs_sort_temp_bytes /
+ * ibgs_scan_temp_bytes bytes. */
+size_t ibgs_sort_temp_bytes(int64_t n, int key_bits, int key_bytes);
+int ibgs_sort_pairs(const void* keys_in, const uint32_t* vals_in, void* keys_out, uint32_t* vals_out, int64_t n,
+                    int key_bits, int key_bytes, void* temp, size_t temp_bytes, void* stream);
+size_t ibgs_scan_temp_bytes(int64_t n);
+int ibgs_scan_gather(int64_t n, const uint32_t* idx, const uint32_t* src, uint32_t* out, void* temp, size_t temp_bytes,
+                     void* stream);
+
 /* State-layout introspection (tests decode the buffers with this, mirroring how the reference's
  * GeometryState/ImageState/BinningState::fromChunk carve theirs, rasterizer_impl.cu:272-316).
  * Writes up to `max` byte offsets; returns the number of arrays in the buffer. `count` is P for GEOM,

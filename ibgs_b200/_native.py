@@ -73,7 +73,7 @@ class IbgsPrologueArgs(C.Structure):
         "opacity", "scales", "rotations", "shs", "all_map",
         "g_opacity", "g_scales", "g_rotations", "g_shs", "g_all_map",
         "d_xyz", "d_opacity_raw", "d_scaling_raw", "d_rotation_raw", "d_features_dc", "d_features_rest",
-        "d_normal_raw", "d_offset")]
+        "d_normal_raw", "d_offset")] + [("smallest_axis_normal", C.c_int32)]
 
 
 class IbgsDepthBatchArgs(C.Structure):

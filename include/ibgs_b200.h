@@ -206,6 +206,11 @@ typedef struct IbgsPrologueArgs {
   /* backward outputs */
   float* d_xyz; float* d_opacity_raw; float* d_scaling_raw; float* d_rotation_raw;
   float* d_features_dc; float* d_features_rest; float* d_normal_raw; float* d_offset;
+  /* learnt_normal = False (gaussian_renderer/__init__.py:305-306, scene/gaussian_model.py:149-161): the plane normal is
+   * the Gaussian's SHORTEST AXIS -- column argmin(scales) of the rotation matrix of the normalised quaternion -- flipped
+   * towards the camera; no offset.  Set it with normal_raw = offset = NULL and all_map != NULL; the normal's gradient
+   * flows into d_rotation_raw (and d_xyz). */
+  int32_t smallest_axis_normal;
 } IbgsPrologueArgs;
 int ibgs_prologue_forward(const IbgsPrologueArgs* args, void* stream);
 int ibgs_prologue_backward(const IbgsPrologueArgs* args, void* stream);

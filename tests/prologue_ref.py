@@ -29,6 +29,32 @@ def torch_prologue(xyz, opacity_raw, scaling_raw, rotation_raw, fdc, frest, norm
     return opacity, scales, rotations, shs, all_map
 
 
+def torch_prologue_smallest_axis(xyz, opacity_raw, scaling_raw, rotation_raw, fdc, frest, V, cam):
+    """learnt_normal=False: get_smallest_axis / get_normal_w_smallest_axis (scene/gaussian_model.py:149-161) with
+    pytorch3d's quaternion_to_matrix, then the same all_map lines without the offset."""
+    opacity = torch.sigmoid(opacity_raw)
+    scales = torch.exp(scaling_raw)
+    rotations = torch.nn.functional.normalize(rotation_raw)
+    shs = torch.cat((fdc, frest), dim=1)
+    r, i, j, k = torch.unbind(rotations, -1)
+    two_s = 2.0 / (rotations * rotations).sum(-1)
+    R = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                     two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                     two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1).reshape(-1, 3, 3)
+    idx = scales.min(dim=-1)[1][..., None, None].expand(-1, 3, -1)
+    normal_global = R.gather(2, idx).squeeze(dim=2)
+    neg_mask = (normal_global * (cam - xyz)).sum(-1) < 0.0
+    normal_global = torch.where(neg_mask[:, None], -normal_global, normal_global)
+    local_normal = normal_global @ V[:3, :3]
+    global_distance = -(normal_global * xyz).sum(-1)
+    local_distance = (global_distance - torch.sum(local_normal * V[[3], :3], dim=1)).abs()
+    all_map = torch.zeros((xyz.shape[0], 5), device=xyz.device, dtype=xyz.dtype)
+    all_map[:, :3] = local_normal
+    all_map[:, 3] = 1.0
+    all_map[:, 4] = local_distance
+    return opacity, scales, rotations, shs, all_map
+
+
 def random_params(P, K=9, seed=0, device="cpu", dtype=torch.float32):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)

@@ -151,3 +151,37 @@ def test_fused_prologue_without_sh_concat_end_to_end():
         assert torch.equal(a, b)
     for k in IN:
         assert _rel(out[0][1][k], out[1][1][k]) <= 1e-4, k   # float atomics: run-to-run summation order
+
+
+@pytest.mark.parametrize("P,K", [(1, 1), (1001, 9), (65_537, 16)])
+def test_fused_prologue_smallest_axis_normal(P, K):
+    """learnt_normal=False (render(..., learnt_normal=False), scene/gaussian_model.py:149-161): plane normal = shortest
+    axis of the Gaussian.  Values and gradients against the reference's torch expressions (float32 autograd) and the
+    float64 oracle; the chosen axis and the flip decision are discrete and must agree exactly."""
+    from ibgs_b200 import fused
+    from oracle import prologue_oracle as O
+    IN6 = IN[:6]
+    p = PR.random_params(P, K=K, seed=P + 1, device="cuda")
+    leaves = {k: p[k].clone().requires_grad_(True) for k in IN6}
+    outs = fused.gaussian_prologue(*[leaves[k] for k in IN6], None, None, p["V"], p["cam"], smallest_axis_normal=True)
+    assert len(outs) == 5
+    tl = {k: p[k].clone().requires_grad_(True) for k in IN6}
+    touts = PR.torch_prologue_smallest_axis(*[tl[k] for k in IN6], p["V"], p["cam"])
+    fw = O.forward_smallest_axis(*[p[k].cpu().numpy() for k in IN6], p["V"].cpu().numpy(), p["cam"].cpu().numpy())
+    for n, o, t in zip(NAMES, outs, touts):
+        assert _rel(o, t) <= 2e-6, (n, _rel(o, t))
+        assert _rel(o, torch.from_numpy(fw[n]).cuda().view_as(o)) <= 2e-6, n
+    g = torch.Generator().manual_seed(4)
+    cots = [torch.randn(o.shape, generator=g).cuda() for o in outs]
+    torch.autograd.backward(list(outs), cots)
+    torch.autograd.backward(list(touts), cots)
+    d = O.backward_smallest_axis(fw, *[c.cpu().numpy() for c in cots])
+    name = dict(fdc="features_dc", frest="features_rest")
+    for k in IN6:
+        if leaves[k].numel() == 0:
+            continue
+        assert _rel(leaves[k].grad, tl[k].grad) <= 1e-5, (k, _rel(leaves[k].grad, tl[k].grad))
+        want = torch.from_numpy(d[name.get(k, k)]).cuda().view_as(leaves[k].grad)
+        assert _rel(leaves[k].grad, want) <= 1e-5, k
+    with pytest.raises(ValueError):
+        fused.gaussian_prologue(*[p[k] for k in IN], p["V"], p["cam"], smallest_axis_normal=True)

@@ -429,7 +429,8 @@ def cpu_baseline(args):
 
 
 # ---- BASELINE metric (ii): training iterations through the reference's unchanged glue ----------------------------------
-def train_step_through_render(impl_name, config, device, rank, world, views_per_rank, steps=2, warmup=1, fused_losses=False):
+def train_step_through_render(impl_name, config, device, rank, world, views_per_rank, steps=2, warmup=1, fused_losses=False,
+                              fast=False):
     """views/s of whole optimisation steps -- `views_per_rank` x train.py:269-370 (render -> L1/SSIM -> normal loss ->
     multi-view photometric loss -> fuse_color + ColorFusionResidualNet -> backward; + AppModel affine and the exposure
     lstsq on cfg4) followed by the optimizer steps of train.py:421-430 -- through the UNCHANGED gaussian_renderer.render
@@ -443,7 +444,9 @@ def train_step_through_render(impl_name, config, device, rank, world, views_per_
     G.prime_depth_cache(w)
     G.make_data_parallel(w)
     fns = None
-    if fused_losses:
+    if fast:          # every section-8f fast path: fused losses, fused-prologue render(), fused colour aggregation (bf16)
+        fns = G.fast_fns(precision="bf16")
+    elif fused_losses:
         import ibgs_b200.loss_utils as FL
         import types
         fns = types.SimpleNamespace(ssim=FL.ssim, compute_photometric_ssim=FL.compute_photometric_ssim)
@@ -475,7 +478,7 @@ def train_step_through_render(impl_name, config, device, rank, world, views_per_
     # iter_time as the reference logs it: one view, render..backward
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    out = G.train_iteration(w, mine[0])
+    out = G.train_iteration(w, mine[0], fns=fns)
     b.record()
     torch.cuda.synchronize(dev)
     w.dp.zero_grad()
@@ -485,7 +488,10 @@ def train_step_through_render(impl_name, config, device, rank, world, views_per_
            "loss": float(out["loss"].item()),
            "stages": "unchanged gaussian_renderer.render() + utils.loss_utils L1/SSIM + normal loss + 3-view photometric "
                      "L1/SSIM + fuse_color/ColorFusionResidualNet + backward; torch.optim.Adam steps every "
-                     f"{total} views" + ("; SSIM terms through ibgs_b200.loss_utils" if fused_losses else "")}
+                     f"{total} views" + ("; SSIM terms through ibgs_b200.loss_utils" if fused_losses and not fast else "")
+                     + ("; FAST PATHS: ibgs_b200.gaussian_renderer.render (fused prologue), ibgs_b200.loss_utils (fused SSIM), "
+                        "ibgs_b200.color_aggregation.fuse_color (fused feature/MLP kernel + channel-padded NHWC bf16 conv "
+                        "decoder) instead of the reference's functions" if fast else "")}
     del w
     gc.collect()
     torch.cuda.empty_cache()
@@ -796,12 +802,14 @@ def main():
                 train[c] = train_step_through_render(args.impl, c, device, rank, eff_world, args.train_views)
             except Exception as ex:  # extra information only: never lose the headline line over it
                 train[c] = {"error": repr(ex)}
-        if args.impl == "b200" and eff_world == 1 and cfgs and not args.no_extras:
-            try:
-                train[cfgs[-1] + "_fused_ssim"] = train_step_through_render(args.impl, cfgs[-1], device, rank, 1,
-                                                                            args.train_views, fused_losses=True)
-            except Exception as ex:
-                train[cfgs[-1] + "_fused_ssim"] = {"error": repr(ex)}
+        if args.impl == "b200" and cfgs and not args.no_extras:
+            # the same step with this repo's section-8f fast paths switched in for the reference's Python glue
+            for c in cfgs:
+                try:
+                    train[c + "_fast"] = train_step_through_render(args.impl, c, device, rank, eff_world, args.train_views,
+                                                                   fast=True)
+                except Exception as ex:
+                    train[c + "_fast"] = {"error": repr(ex)}
 
     if rank != 0:
         if eff_world > 1:

@@ -93,6 +93,12 @@ class IbgsSsimArgs(C.Structure):
         ("dL_dmap_is_scalar", C.c_int32), ("dL_dmap_scale", C.c_float), ("dL_dimg1", _fp), ("dL_dimg2", _fp)]
 
 
+class IbgsColorFeatArgs(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("height", "width", "n_views", "mode", "channel_pitch", "bf16")] + [
+        (k, _fp) for k in ("warped", "cam_feat", "rendered", "camera_ray", "w1", "b1", "w2", "b2", "cnn_input",
+                           "g_cnn_input", "d_warped", "d_rendered", "d_w1", "d_b1", "d_w2", "d_b2")]
+
+
 ADAM_MAX_GROUPS = 16
 
 
@@ -115,6 +121,7 @@ EXPORTS = [
     "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
     "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward", "ibgs_adam_step", "ibgs_set_backward_variant", "ibgs_set_forward_variant",
     "ibgs_sort_temp_bytes", "ibgs_sort_pairs", "ibgs_scan_temp_bytes", "ibgs_scan_gather",
+    "ibgs_color_features_forward", "ibgs_color_features_backward",
 ]
 
 
@@ -162,6 +169,9 @@ def _load():
     for fn in (lib.ibgs_ssim_forward, lib.ibgs_ssim_backward):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(IbgsSsimArgs), C.c_void_p]
+    for fn in (lib.ibgs_color_features_forward, lib.ibgs_color_features_backward):
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(IbgsColorFeatArgs), C.c_void_p]
     for fn in (lib.ibgs_set_backward_variant, lib.ibgs_set_forward_variant):
         fn.restype = C.c_int
         fn.argtypes = [C.c_int]

@@ -63,7 +63,8 @@ double g_prof_ms[PROF_COUNT] = {0};
 long long g_prof_n[PROF_COUNT] = {0};
 const char* g_prof_names[PROF_COUNT] = {"preprocess", "depth_order_sort", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
                                         "texture_fill", "render_forward", "render_backward", "preprocess_backward",
-                                        "ssim_forward", "ssim_backward", "tile_sort_histograms"};
+                                        "ssim_forward", "ssim_backward", "tile_sort_histograms",
+                                        "color_features_forward", "color_features_backward"};
 void prof_drain() {
   for (auto& p : g_prof_pending) {
     float ms = 0.f;

@@ -303,6 +303,37 @@ typedef struct IbgsAdamArgs {
 } IbgsAdamArgs;
 int ibgs_adam_step(const IbgsAdamArgs* args, void* stream);
 
+/* Colour-aggregation front half (optional fast path).  Replaces, in ONE launch per direction,
+ * the feature assembly of fuse_color (color_aggregation_network.py:196-206: valid = sum of a view's 4 camera features > 0,
+ * residual = (warped - rendered) * valid, x = [residual, cam_feat]) and ColorFusionResidualNet.forward up to the conv
+ * decoder's input (:121-131: per_view_mlp = Linear(7,32) ReLU Linear(32,32) ReLU per (pixel, view), mean / max over the
+ * views, cat with ray_dir and c_3dgs).  The output is the decoder's input in NHWC with `channel_pitch` channels per pixel
+ * (0..31 aggregated features, 32..34 ray, 35..37 rendered colour, the rest zero), float32 or bf16.
+ * The backward recomputes the hidden layers; weight gradients are ACCUMULATED (atomicAdd) into d_w1 / d_b1 / d_w2 / d_b2
+ * (the caller zeroes them), d_warped / d_rendered are written (either may be NULL: the detached case of :171-177). */
+typedef struct IbgsColorFeatArgs {
+  int32_t height, width;
+  int32_t n_views;            /* nb_valid_warp_level, 1..5 */
+  int32_t mode;               /* 0 = mean, 1 = max (feat_aggregate_mode) */
+  int32_t channel_pitch;      /* multiple of 8, >= 40 */
+  int32_t bf16;               /* cnn_input / g_cnn_input element type: 1 = bf16, 0 = float32 */
+  const float* warped;        /* [n_views][3][H*W]  first n_views of out_warped_image */
+  const float* cam_feat;      /* [n_views][4][H*W]  first n_views of out_cam_feat */
+  const float* rendered;      /* [3][H*W] */
+  const float* camera_ray;    /* [3][H*W] */
+  const float* w1;            /* per_view_mlp[0].weight [32][7] */
+  const float* b1;            /* [32] */
+  const float* w2;            /* per_view_mlp[2].weight [32][32] */
+  const float* b2;            /* [32] */
+  void* cnn_input;            /* forward output [H*W][channel_pitch] */
+  const void* g_cnn_input;    /* backward input  [H*W][channel_pitch] */
+  float* d_warped;            /* backward output [n_views][3][H*W] or NULL */
+  float* d_rendered;          /* backward output [3][H*W] or NULL */
+  float* d_w1; float* d_b1; float* d_w2; float* d_b2;   /* backward, accumulated */
+} IbgsColorFeatArgs;
+int ibgs_color_features_forward(const IbgsColorFeatArgs* args, void* stream);
+int ibgs_color_features_backward(const IbgsColorFeatArgs* args, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds -- cgo / JNI / ctypes on plain host arrays;
  * exercised by tests/test_gpu_host_api.py against the device entry points):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages

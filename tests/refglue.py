@@ -295,12 +295,15 @@ def prime_depth_cache(w):
 def train_iteration(w, cam_idx, loss_scale=1.0, fns=None):
     """Body of the training loop the reference times as `iter_time` (train.py:269-370): render -> image loss ->
     single-view normal loss -> multi-view photometric loss -> colour-aggregation prediction + loss -> backward.
-    `fns` may override ssim / compute_photometric_ssim / l1_loss (the fused-SSIM fast path); default = the reference's."""
+    `fns` may override ssim / compute_photometric_ssim / l1_loss (the fused-SSIM fast path) and render / fuse_color
+    (ibgs_b200.gaussian_renderer / ibgs_b200.color_aggregation); default = the reference's."""
     g, opt = w.glue, w.opt
     LU = g.loss_utils
     ssim = getattr(fns, "ssim", LU.ssim)
     l1_loss = getattr(fns, "l1_loss", LU.l1_loss)
     photo_ssim = getattr(fns, "compute_photometric_ssim", LU.compute_photometric_ssim)
+    render = getattr(fns, "render", g.render)
+    fuse_color = getattr(fns, "fuse_color", g.fuse_color)
     iteration = w.iteration
     gaussians = w.gaussians
     cams = w.scene.getTrainCameras()
@@ -309,8 +312,8 @@ def train_iteration(w, cam_idx, loss_scale=1.0, fns=None):
     if iteration > 1000 and opt.exposure_compensation:
         gaussians.use_app = True
     geo = iteration > opt.single_view_weight_from_iter - len(cams) * 2
-    render_pkg = g.render(viewpoint_cam, gaussians, w.scene, w.pipe, w.args, w.background, render_geo=geo,
-                          return_depth_normal=geo, **render_kwargs(w))
+    render_pkg = render(viewpoint_cam, gaussians, w.scene, w.pipe, w.args, w.background, render_geo=geo,
+                        return_depth_normal=geo, **render_kwargs(w))
     image = render_pkg["render"]
     if geo:
         w.scene.rendered_depth_list[cam_idx] = render_pkg["median_intersected_depth"].detach().to(device=w.args.data_device)
@@ -351,8 +354,8 @@ def train_iteration(w, cam_idx, loss_scale=1.0, fns=None):
     aggregate_image_loss = torch.tensor(0.0).float().cuda()
     fusion = None
     if opt.use_color_aggregation and iteration > opt.start_color_aggregation_iter:
-        fusion = g.fuse_color(render_pkg, color_aggregation_network=w.color_net, iter_count=w.color_iter_count,
-                              burn_start=w.color_burn_start, burn_end=w.color_burn_end, iteration=iteration, opts=opt)
+        fusion = fuse_color(render_pkg, color_aggregation_network=w.color_net, iter_count=w.color_iter_count,
+                            burn_start=w.color_burn_start, burn_end=w.color_burn_end, iteration=iteration, opts=opt)
         if fusion is not None:
             image_pred = fusion["image_pred"]
             aggregate_image_loss = ((1.0 - opt.lambda_dssim) * l1_loss(image_pred, gt_image)
@@ -389,6 +392,23 @@ def optimizer_step(w):
         w.color_opt.step()
         w.color_opt.zero_grad()
         w.color_iter_count += 1
+
+
+def fast_fns(precision="bf16", losses=True, renderer=True, color=True):
+    """The section-8f fast paths of ibgs_b200 as `fns` for train_iteration: fused SSIM losses, the fused-prologue render()
+    and the fused colour-aggregation step."""
+    import functools
+    f = types.SimpleNamespace()
+    if losses:
+        import ibgs_b200.loss_utils as FL
+        f.ssim, f.compute_photometric_ssim = FL.ssim, FL.compute_photometric_ssim
+    if renderer:
+        import ibgs_b200.gaussian_renderer as FR
+        f.render = FR.render
+    if color:
+        import ibgs_b200.color_aggregation as CA
+        f.fuse_color = functools.partial(CA.fuse_color, precision=precision)
+    return f
 
 
 GAUSSIAN_PARAMS = ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation", "_normal", "_offset")

@@ -48,6 +48,9 @@ def test_struct_layouts_match_header(tmp_path):
               ("offsetof(IbgsAdamArgs, groups)", N.IbgsAdamArgs.groups.offset),
               ("offsetof(IbgsAdamArgs, step)", N.IbgsAdamArgs.step.offset),
               ("offsetof(IbgsAdamArgs, zero_grads)", N.IbgsAdamArgs.zero_grads.offset),
+              ("sizeof(IbgsColorFeatArgs)", C.sizeof(N.IbgsColorFeatArgs)),
+              ("offsetof(IbgsColorFeatArgs, warped)", N.IbgsColorFeatArgs.warped.offset),
+              ("offsetof(IbgsColorFeatArgs, d_b2)", N.IbgsColorFeatArgs.d_b2.offset),
               ("IBGS_MAX_DEPTH_BATCH", N.MAX_DEPTH_BATCH), ("IBGS_ADAM_MAX_GROUPS", N.ADAM_MAX_GROUPS),
               ("IBGS_MAX_SRC", N.MAX_SRC), ("IBGS_MAX_BUFFER_LENGTH", N.MAX_BUFFER_LENGTH)]
     prog = tmp_path / "sz.c"

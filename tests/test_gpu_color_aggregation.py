@@ -1,0 +1,142 @@
+"""GPU: the colour-aggregation fast path (ibgs_b200.color_aggregation -> C ABI -> color_features.cu + padded NHWC conv
+decoder) against (a) the float64 oracle, (b) the reference's own torch expressions on its unchanged module, and (c) the
+reference's whole fuse_color (color_aggregation_network.py:156-250): values and gradients."""
+import numpy as np
+import pytest
+import torch
+
+import colorfeat_ref as CR
+import refglue as G
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not G.available(), reason="reference glue not staged")]
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _net(H, W, mode="mean", seed=3):
+    G._paths()
+    import color_aggregation_network as CAN
+    torch.manual_seed(seed)
+    return CAN, CAN.ColorFusionResidualNet(height=H, width=W, feat_aggregate_mode=mode).cuda()
+
+
+@pytest.mark.parametrize("H,W,nv,mode", [(7, 5, 1, "mean"), (37, 53, 3, "mean"), (64, 96, 2, "max"), (33, 31, 4, "max"),
+                                         (120, 200, 3, "mean")])
+def test_color_features_kernel_fp32(H, W, nv, mode):
+    """Kernel in float32 storage vs the float64 oracle and vs torch autograd of the reference's expressions."""
+    from ibgs_b200 import color_aggregation as CA
+    from oracle import color_features_oracle as O
+    CAN, net = _net(H, W, mode)
+    pkg = CR.random_render_pkg(H, W, M=4, seed=H * W, device="cuda")
+    N = H * W
+    # forward values are continuous in the inputs; gradients are not: a ReLU pre-activation within rounding of zero (or,
+    # in max mode, two views within rounding of each other) flips a 0/1 factor between two float32 evaluation orders.
+    # Small cases (no such event in ~1e5 hidden units) are held to float32 rounding, large ones allow a few flips.
+    gtol = 2e-5 if (N * nv < 8000 and mode == "mean") else 3e-3
+    leaves = {k: pkg[k].clone().requires_grad_(True) for k in ("render", "warped_image")}
+    x = CA.color_features(leaves["warped_image"], pkg["cam_feat"], leaves["render"], pkg["camera_ray"].view(3, H, W),
+                          net.per_view_mlp, nv, mode=mode, bf16=False)
+    assert x.shape == (1, 40, H, W) and x.is_contiguous(memory_format=torch.channels_last)
+    assert not x[:, 38:].any()
+    tl = {k: pkg[k].clone().requires_grad_(True) for k in ("render", "warped_image")}
+    want = CR.torch_color_features(net, dict(pkg, **tl), nv)
+    assert _rel(x[:, :38], want) <= 2e-6
+    l1, l2 = net.per_view_mlp[0], net.per_view_mlp[2]
+    c = lambda t: t.detach().cpu().numpy()
+    out, cache = O.forward(c(pkg["warped_image"]).reshape(4, 3, N), c(pkg["cam_feat"]).reshape(4, 4, N),
+                           c(pkg["render"]).reshape(3, N), c(pkg["camera_ray"]), c(l1.weight), c(l1.bias), c(l2.weight),
+                           c(l2.bias), nv, mode)
+    assert _rel(x[0, :38].reshape(38, N).T, torch.from_numpy(out).cuda()) <= 2e-6
+    g = torch.randn((1, 38, H, W), generator=torch.Generator().manual_seed(1)).cuda()
+    net.zero_grad()
+    x[:, :38].backward(g)
+    mine = [p.grad.clone() for p in (l1.weight, l1.bias, l2.weight, l2.bias)]
+    net.zero_grad()
+    want.backward(g)
+    theirs = [p.grad.clone() for p in (l1.weight, l1.bias, l2.weight, l2.bias)]
+    d_warped, d_rendered, dw1, db1, dw2, db2 = O.backward(cache, c(g[0]).reshape(38, N).T)
+    for got, t, o in zip(mine, theirs, (dw1, db1, dw2, db2)):
+        assert _rel(got, t) <= gtol, _rel(got, t)
+        assert _rel(got, torch.from_numpy(o).cuda().view_as(got)) <= gtol
+    assert _rel(leaves["render"].grad, tl["render"].grad) <= gtol
+    assert _rel(leaves["warped_image"].grad, tl["warped_image"].grad) <= gtol
+    assert _rel(leaves["render"].grad.view(3, N), torch.from_numpy(d_rendered).cuda()) <= gtol
+    assert not leaves["warped_image"].grad.view(4, 3, N)[nv:].any()
+
+
+def test_color_features_kernel_bf16_storage():
+    from ibgs_b200 import color_aggregation as CA
+    H, W, nv = 48, 80, 3
+    CAN, net = _net(H, W)
+    pkg = CR.random_render_pkg(H, W, seed=5, device="cuda")
+    x32 = CA.color_features(pkg["warped_image"], pkg["cam_feat"], pkg["render"], pkg["camera_ray"].view(3, H, W),
+                            net.per_view_mlp, nv, bf16=False)
+    x16 = CA.color_features(pkg["warped_image"], pkg["cam_feat"], pkg["render"], pkg["camera_ray"].view(3, H, W),
+                            net.per_view_mlp, nv, bf16=True)
+    assert x16.dtype == torch.bfloat16 and x16.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(x16, x32.to(torch.bfloat16))          # same arithmetic, rounded once at the store
+
+
+class _Opts:
+    enable_exposure_correction = False
+    nb_visible_src_frames = 3
+    residual_resolution_scale = 1.0
+
+
+@pytest.mark.parametrize("exposure,burn,dead", [(False, 1.0, 0), (True, 1.0, 0), (False, 0.6, 0), (False, 1.0, 2)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_fuse_color_vs_reference(exposure, burn, dead, precision):
+    """Whole fuse_color, fast path vs the reference's function on the same unchanged module: result dict and the
+    gradients of a loss on image_pred with respect to the rasterizer outputs and every network parameter."""
+    from ibgs_b200 import color_aggregation as CA
+    H, W = 90, 134
+    CAN, net = _net(H, W)
+    opts = _Opts()
+    opts.enable_exposure_correction = exposure
+    pkg = CR.random_render_pkg(H, W, seed=17, device="cuda", dead_views=dead)
+    # iter_count chosen so that burned_in_gauss == burn
+    it, b0, b1 = (None, None, None) if burn == 1.0 else (int((2 * burn - 1) * 1000), 0, 1000)
+    gt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(2)).cuda()
+    res = {}
+    for name, fn in (("ref", CAN.fuse_color), ("fast", lambda *a, **k: CA.fuse_color(*a, precision=precision, **k))):
+        leaves = {k: pkg[k].clone().requires_grad_(True) for k in ("render", "warped_image")}
+        net.zero_grad()
+        out = fn(dict(pkg, **leaves), color_aggregation_network=net, iter_count=it, burn_start=b0, burn_end=b1,
+                 iteration=20000, opts=opts)
+        (out["image_pred"] - gt).abs().mean().backward()
+        res[name] = (out, {k: v.grad for k, v in leaves.items()}, [p.grad.clone() for p in net.parameters()])
+    ro, rg, rp = res["ref"]
+    fo, fg, fp = res["fast"]
+    assert fo["nb_valid_warp_level"] == ro["nb_valid_warp_level"] == (3 if dead < 2 else 2)
+    assert fo["burned_in_gauss"] == ro["burned_in_gauss"]
+    assert torch.equal(fo["valid_warp_mask"], ro["valid_warp_mask"])
+    assert torch.equal(fo["warped_image_list"], ro["warped_image_list"])
+    # the reference's convolutions run in tf32 by default (torch.backends.cudnn.allow_tf32): ~1e-3 of noise either way
+    tol_v, tol_g = (3e-3, 3e-2) if precision == "fp32" else (2e-2, 8e-2)
+    assert (fo["image_pred"] - ro["image_pred"]).abs().max().item() <= tol_v
+    assert (fo["residual"] - ro["residual"]).abs().max().item() <= tol_v
+    for a, b in zip(fp, rp):
+        assert _rel(a, b) <= tol_g, _rel(a, b)
+    if burn < 1.0:     # gradients to the Gaussians are blocked while the residual is burning in (:170-177)
+        assert all(g is None for g in fg.values()) and all(g is None for g in rg.values())
+    else:
+        for k in fg:
+            assert _rel(fg[k], rg[k]) <= tol_g, (k, _rel(fg[k], rg[k]))
+
+
+def test_fast_path_argument_errors():
+    from ibgs_b200 import color_aggregation as CA
+    H, W = 16, 16
+    CAN, net = _net(H, W)
+    pkg = CR.random_render_pkg(H, W, device="cuda")
+    opts = _Opts()
+    opts.residual_resolution_scale = 0.5
+    with pytest.raises(NotImplementedError):
+        CA.fuse_color(pkg, net, None, None, None, 1, opts)
+    assert CA.fuse_color(pkg, None, None, None, None, 1, _Opts()) is None
+    with pytest.raises(RuntimeError):
+        CA.color_features(pkg["warped_image"].cpu(), pkg["cam_feat"].cpu(), pkg["render"].cpu(),
+                          pkg["camera_ray"].view(3, H, W).cpu(), net.per_view_mlp, 3)

@@ -9,13 +9,13 @@
 // How (this project's own decomposition, on this project's own sort / scan primitives, sort.cu -- no library code).
 // A 64-bit LSD sort of all R instances is 6 passes over 24-byte pairs at R = 15 M.  The depth half of the key is a
 // property of the GAUSSIAN, not of the instance, so it is sorted once per Gaussian instead of once per instance:
-//   1. stable sort of the P Gaussians by depth bits (32-bit keys, P << R items, three 11/11/10-bit multisplit passes);
+//   1. stable sort of the P Gaussians by depth bits (32-bit keys, P << R items, four 8-bit passes of sort.cu);
 //      culled Gaussians carry the key 0xFFFFFFFF and land behind every visible one;
 //   2. inclusive scan of tiles_touched in that order -> write offsets; offsets[P-1] = num_rendered;
 //   3. emission in depth order: instance = (tile id u16/u32, Gaussian id u32), warp-cooperative for big rectangles;
-//   4. stable sort of the R instances by tile id only: ONE multisplit pass with 2^13 bins at 1080p (two above 8192
-//      tiles or in batched depth renders);
-//   5. tile ranges: a by-product of the sort's bin totals (one pass) or identify_tile_ranges_kernel (two passes).
+//   4. stable sort of the R instances by tile id only: ceil(msb(T) / 8) passes (two at 1080p: 13 bits -> 7 + 6) over
+//      (u16 tile, u32 id) pairs -- (u32, u32) above 65536 tiles or in batched depth renders;
+//   5. tile ranges: identify_tile_ranges_kernel on the sorted tile ids (a single-pass sort emits them itself).
 // Stability of (4) keeps each tile's instances in emission order = ascending depth bits, ties in ascending
 // Gaussian id (stability of (1)) -- exactly the reference's order.  The reference's sorted 64-bit keys are
 // (tile id << 32 | depth bits of point_list[i]); tests rebuild them from this state and compare bit-exactly.

@@ -10,6 +10,8 @@ this module is what a caller switches to when it also wants the Python prologue 
   * activations + plane normal / distance (`all_map`) come from ONE fused launch per direction (ibgs_b200.fused: sigmoid /
     exp / normalize / normal flip / plane distance, learnt normal or shortest axis) instead of ~30 torch kernels, and the
     SH coefficients are read in place (`shs` = _features_dc, `shs_rest` = _features_rest) instead of through torch.cat;
+    leaves that already hold a `.grad` (a view batch accumulating into an arena) get their gradient ADDED by the
+    backward kernel itself (`accumulate_grads`) instead of through a temporary + autograd's add pass;
   * with do_render_src_depth the source-view depths are rendered by ONE batched depth-only pass
     (ibgs_b200.depth_batch.render_depth_views) instead of one rasterizer call per source view (:245-252);
   * the depth-to-normal map (utils/graphics_utils.py:38-75 through render_normal, :15-26) is evaluated from the pinhole
@@ -190,7 +192,7 @@ def render(viewpoint_camera, pc, scene, pipe, args, bg_color, learnt_normal: boo
     (rendered_image, radii, out_normal_map, out_median_intersected_depth, out_cam_feat, out_warped_image,
      out_min_depth_diff, out_camera_ray, use_first_src_frame_mask) = rasterizer(
         means3D=xyz, means2D=screenspace_points, means2D_abs=screenspace_points_abs, opacities=opacity, scales=scales,
-        rotations=rotations, all_map=input_all_map, cov3D_precomp=None, **sh_kw)
+        rotations=rotations, all_map=input_all_map, cov3D_precomp=None, accumulate_grads=True, **sh_kw)
 
     rendered_normal = out_normal_map[0:3] if render_geo else None
     if return_depth_normal:

@@ -429,7 +429,7 @@ def cpu_baseline(args):
 
 
 # ---- BASELINE metric (ii): training iterations through the reference's unchanged glue ----------------------------------
-def train_step_through_render(impl_name, config, device, rank, world, views_per_rank, steps=2, warmup=1, fused_losses=False,
+def train_step_through_render(impl_name, config, device, rank, world, views_per_rank, steps=3, warmup=2, fused_losses=False,
                               fast=False):
     """views/s of whole optimisation steps -- `views_per_rank` x train.py:269-370 (render -> L1/SSIM -> normal loss ->
     multi-view photometric loss -> fuse_color + ColorFusionResidualNet -> backward; + AppModel affine and the exposure

@@ -101,16 +101,18 @@ __device__ __forceinline__ void layer2_add_2(const Weights& s, int j, f2 h, f2 a
     acc[i + 3] = __ffma2_rn(bc2(w.w), h, acc[i + 3]);
   }
 }
-__device__ __forceinline__ void layer2_add(const Weights& s, int j, float h, float acc[F]) {
+// one view, outputs packed in pairs (acc[i / 2] = features i, i + 1): two outputs per FFMA2, the weight pair is the
+// register pair the LDS.128 delivered
+__device__ __forceinline__ void layer2_add(const Weights& s, int j, float h, f2 acc[F / 2]) {
+  const f2 hh = bc2(h);
 #pragma unroll
   for (int i = 0; i < F; i += 4) {
     const float4 w = *reinterpret_cast<const float4*>(&s.w2t[j][i]);
-    acc[i] = fmaf(w.x, h, acc[i]);
-    acc[i + 1] = fmaf(w.y, h, acc[i + 1]);
-    acc[i + 2] = fmaf(w.z, h, acc[i + 2]);
-    acc[i + 3] = fmaf(w.w, h, acc[i + 3]);
+    acc[i / 2] = __ffma2_rn(make_float2(w.x, w.y), hh, acc[i / 2]);
+    acc[i / 2 + 1] = __ffma2_rn(make_float2(w.z, w.w), hh, acc[i / 2 + 1]);
   }
 }
+__device__ __forceinline__ float& el(f2* a, int i) { return (i & 1) ? a[i >> 1].y : a[i >> 1].x; }
 
 template <bool BF16>
 __device__ __forceinline__ void store_channels(void* out, size_t p, int CP, const float agg[F], const float ray[3],
@@ -188,8 +190,7 @@ constexpr int BW_WARPS = 4;
 constexpr int PITCH = 36;   // floats per staged row: 16-byte aligned, (4 p + c) mod 32 spreads a quarter-warp's STS.128
 struct WarpTile {
   float h1[32][PITCH];      // relu(layer 1) of the warp's 32 pixels (one view)
-  float g2[32][PITCH];      // gradient at layer 2's pre-activation
-  float g1[32][PITCH];      // gradient at layer 1's pre-activation
+  float g[32][PITCH];       // gradient at layer 2's pre-activation (pass A), then at layer 1's (pass B)
   float x[32][8];
 };
 struct BwdShared {
@@ -233,7 +234,7 @@ __device__ __forceinline__ void load_grad(const void* g, size_t p, int CP, float
 }
 
 template <bool BF16>
-__global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kernel(const CfArgs a) {
+__global__ void __launch_bounds__(32 * BW_WARPS, 4) color_features_backward_kernel(const CfArgs a) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   BwdShared& s = *reinterpret_cast<BwdShared*>(s_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,11 +244,12 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kern
   const float inv_v = 1.0f / (float)a.V;
 
   // this lane's slices of the weight gradients: column `lane` of dW2, row `lane` of dW1, element `lane` of the biases
-  float dw2c[F], dw1r[8], db1 = 0.f, db2 = 0.f;
+  f2 dw2c[F / 2], dw1r[4];
+  float db1 = 0.f, db2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < F; i++) dw2c[i] = 0.f;
+  for (int i = 0; i < F / 2; i++) dw2c[i] = bc2(0.f);
 #pragma unroll
-  for (int k = 0; k < 8; k++) dw1r[k] = 0.f;
+  for (int k = 0; k < 4; k++) dw1r[k] = bc2(0.f);
 
   const int nbatch = (a.N + 31) / 32;
   for (int batch = blockIdx.x * BW_WARPS + warp; batch < nbatch; batch += gridDim.x * BW_WARPS) {
@@ -271,15 +273,15 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kern
       for (int v = 0; v < a.V; v++) {
         float xa[8];
         load_x(a, v, pc, rend, xa);
-        float acc[F];
+        f2 acc[F / 2];
 #pragma unroll
-        for (int i = 0; i < F; i++) acc[i] = s.w.b2[i];
+        for (int i = 0; i < F; i++) el(acc, i) = s.w.b2[i];
 #pragma unroll 2
         for (int j = 0; j < F; j++) layer2_add(s.w, j, hidden1(s.w, j, xa), acc);
 #pragma unroll
         for (int i = 0; i < F; i++) {
-          if (acc[i] > best[i]) {
-            best[i] = acc[i];
+          if (el(acc, i) > best[i]) {
+            best[i] = el(acc, i);
             arg_b[i >> 3] = (arg_b[i >> 3] & ~(0xfu << (4 * (i & 7)))) | ((uint32_t)v << (4 * (i & 7)));
           }
         }
@@ -289,11 +291,11 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kern
     for (int v = 0; v < a.V; v++) {
       float x[8];
       const float valid = load_x(a, v, pc, rend, x);
-      __syncwarp();   // the previous view's outer-product pass is done with the tile
+      __syncwarp();   // the previous view's pass B is done with the tile
       // recompute: hidden layer 1 goes straight into this lane's row of the staging tile, layer 2 accumulates
-      float g2[F];
+      f2 g2[F / 2];
 #pragma unroll
-      for (int i = 0; i < F; i++) g2[i] = s.w.b2[i];
+      for (int i = 0; i < F; i++) el(g2, i) = s.w.b2[i];
       for (int j0 = 0; j0 < F; j0 += 4) {
         float h[4];
 #pragma unroll
@@ -307,8 +309,28 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kern
 #pragma unroll
       for (int i = 0; i < F; i++) {
         const float g = a.mode == 0 ? ga[i] * inv_v : (((arg_b[i >> 3] >> (4 * (i & 7))) & 0xfu) == (uint32_t)v ? ga[i] : 0.f);
-        g2[i] = g2[i] > 0.f ? g : 0.f;
+        el(g2, i) = el(g2, i) > 0.f ? g : 0.f;
       }
+      // stage g2 and x next to h1, then pass A: dW2 += g2 (x) h1 over the warp's 32 pixels
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        *reinterpret_cast<float4*>(&t.g[lane][4 * q]) = make_float4(g2[2 * q].x, g2[2 * q].y, g2[2 * q + 1].x, g2[2 * q + 1].y);
+      *reinterpret_cast<float4*>(&t.x[lane][0]) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(&t.x[lane][4]) = make_float4(x[4], x[5], x[6], 0.f);
+      __syncwarp();
+      // (a dead lane's g2 / g1 rows are exact zeros: ga was zeroed)
+#pragma unroll 4
+      for (int q = 0; q < 32; q++) {
+        const float hj = t.h1[q][lane];
+        db2 += t.g[q][lane];
+#pragma unroll
+        for (int i = 0; i < F; i += 4) {
+          const float4 g = *reinterpret_cast<const float4*>(&t.g[q][i]);
+          dw2c[i / 2] = __ffma2_rn(make_float2(g.x, g.y), bc2(hj), dw2c[i / 2]);
+          dw2c[i / 2 + 1] = __ffma2_rn(make_float2(g.z, g.w), bc2(hj), dw2c[i / 2 + 1]);
+        }
+      }
+      __syncwarp();   // every lane is done with the g2 rows: the same tile now takes g1
       // g1[j] = relu'(h1[j]) * sum_i w2[i][j] g2[i];  d x[0..2] = sum_j w1[j][c] g1[j]  -> residual -> warped / rendered
       float dx[3] = {0.f, 0.f, 0.f};
       for (int j0 = 0; j0 < F; j0 += 4) {
@@ -317,22 +339,21 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kern
         float g1[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          float acc0 = 0.f, acc1 = 0.f;
+          f2 acc0 = bc2(0.f), acc1 = bc2(0.f);
 #pragma unroll
           for (int i = 0; i < F; i += 4) {
             const float4 w = *reinterpret_cast<const float4*>(&s.w.w2t[j0 + u][i]);
-            acc0 = fmaf(w.x, g2[i], acc0);
-            acc1 = fmaf(w.y, g2[i + 1], acc1);
-            acc0 = fmaf(w.z, g2[i + 2], acc0);
-            acc1 = fmaf(w.w, g2[i + 3], acc1);
+            acc0 = __ffma2_rn(make_float2(w.x, w.y), g2[i / 2], acc0);
+            acc1 = __ffma2_rn(make_float2(w.z, w.w), g2[i / 2 + 1], acc1);
           }
-          g1[u] = hh[u] > 0.f ? acc0 + acc1 : 0.f;
+          const f2 sum2 = __fadd2_rn(acc0, acc1);
+          g1[u] = hh[u] > 0.f ? sum2.x + sum2.y : 0.f;
           const float4 w = *reinterpret_cast<const float4*>(&s.w.w1[j0 + u][0]);
           dx[0] = fmaf(w.x, g1[u], dx[0]);
           dx[1] = fmaf(w.y, g1[u], dx[1]);
           dx[2] = fmaf(w.z, g1[u], dx[2]);
         }
-        *reinterpret_cast<float4*>(&t.g1[lane][j0]) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+        *reinterpret_cast<float4*>(&t.g[lane][j0]) = make_float4(g1[0], g1[1], g1[2], g1[3]);
       }
 #pragma unroll
       for (int c = 0; c < 3; c++) {
@@ -340,34 +361,18 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kern
         if (a.d_warped && live) a.d_warped[(3 * (size_t)v + c) * a.N + p] = d;
         drend[c] -= d;
       }
-      // stage the rest of this view's rows for the weight-gradient outer products
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        *reinterpret_cast<float4*>(&t.g2[lane][4 * q]) = make_float4(g2[4 * q], g2[4 * q + 1], g2[4 * q + 2], g2[4 * q + 3]);
-      *reinterpret_cast<float4*>(&t.x[lane][0]) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(&t.x[lane][4]) = make_float4(x[4], x[5], x[6], 0.f);
       __syncwarp();
-      // (a dead lane's g2 / g1 rows are exact zeros: ga was zeroed)
+      // pass B: dW1 += g1 (x) x
 #pragma unroll 4
       for (int q = 0; q < 32; q++) {
-        const float hj = t.h1[q][lane];
-        const float g1i = t.g1[q][lane];
-        db2 += t.g2[q][lane];
+        const float g1i = t.g[q][lane];
         db1 += g1i;
-#pragma unroll
-        for (int i = 0; i < F; i += 4) {
-          const float4 g = *reinterpret_cast<const float4*>(&t.g2[q][i]);
-          dw2c[i] = fmaf(g.x, hj, dw2c[i]);
-          dw2c[i + 1] = fmaf(g.y, hj, dw2c[i + 1]);
-          dw2c[i + 2] = fmaf(g.z, hj, dw2c[i + 2]);
-          dw2c[i + 3] = fmaf(g.w, hj, dw2c[i + 3]);
-        }
         const float4 xa = *reinterpret_cast<const float4*>(&t.x[q][0]);
         const float4 xb = *reinterpret_cast<const float4*>(&t.x[q][4]);
-        dw1r[0] = fmaf(g1i, xa.x, dw1r[0]); dw1r[1] = fmaf(g1i, xa.y, dw1r[1]);
-        dw1r[2] = fmaf(g1i, xa.z, dw1r[2]); dw1r[3] = fmaf(g1i, xa.w, dw1r[3]);
-        dw1r[4] = fmaf(g1i, xb.x, dw1r[4]); dw1r[5] = fmaf(g1i, xb.y, dw1r[5]);
-        dw1r[6] = fmaf(g1i, xb.z, dw1r[6]);
+        dw1r[0] = __ffma2_rn(bc2(g1i), make_float2(xa.x, xa.y), dw1r[0]);
+        dw1r[1] = __ffma2_rn(bc2(g1i), make_float2(xa.z, xa.w), dw1r[1]);
+        dw1r[2] = __ffma2_rn(bc2(g1i), make_float2(xb.x, xb.y), dw1r[2]);
+        dw1r[3] = __ffma2_rn(bc2(g1i), make_float2(xb.z, xb.w), dw1r[3]);
       }
     }
     if (a.d_rendered && live) {
@@ -381,9 +386,9 @@ __global__ void __launch_bounds__(32 * BW_WARPS, 3) color_features_backward_kern
   float* red = reinterpret_cast<float*>(&s.tile[0]);   // [BW_WARPS][F + 8 + 2][32]
   constexpr int ROWS = F + 8 + 2;
 #pragma unroll
-  for (int i = 0; i < F; i++) red[(warp * ROWS + i) * 32 + lane] = dw2c[i];
+  for (int i = 0; i < F; i++) red[(warp * ROWS + i) * 32 + lane] = el(dw2c, i);
 #pragma unroll
-  for (int k = 0; k < 8; k++) red[(warp * ROWS + F + k) * 32 + lane] = dw1r[k];
+  for (int k = 0; k < 8; k++) red[(warp * ROWS + F + k) * 32 + lane] = el(dw1r, k);
   red[(warp * ROWS + F + 8) * 32 + lane] = db1;
   red[(warp * ROWS + F + 9) * 32 + lane] = db2;
   __syncthreads();
@@ -468,7 +473,7 @@ extern "C" int ibgs_color_features_backward(const IbgsColorFeatArgs* a, void* st
   if ((uintptr_t)a->g_cnn_input % 16) { ibgs_set_error("g_cnn_input must be 16-byte aligned"); return IBGS_EINVAL; }
   const int smem = (int)sizeof(BwdShared);
   const int nbatch = (c.N + 31) / 32;
-  const int blocks = min((nbatch + BW_WARPS - 1) / BW_WARPS, sm_count() * 3);
+  const int blocks = min((nbatch + BW_WARPS - 1) / BW_WARPS, sm_count() * 4);
   ProfScope prof(PROF_COLORFEAT_BWD, s);
   if (a->bf16) {
     CUDA_TRY(cudaFuncSetAttribute(color_features_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -435,7 +435,8 @@ def dp_train_step(w, cam_indices, views_total, fns=None, sync_stats=False):
     outs = []
     for ci in cam_indices:
         out = train_iteration(w, ci, fns=fns)
-        densification_stats(w, out)
+        if w.iteration < w.opt.densify_until_iter or sync_stats:     # train.py:399: only while densification is on
+            densification_stats(w, out)
         outs.append(out)
     dp.all_reduce_grads(views_total=views_total)
     dp.sync_depth_cache(w.scene.rendered_depth_list, cam_indices)

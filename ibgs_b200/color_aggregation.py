@@ -125,6 +125,29 @@ def _padded_weight(conv, in_segments, dtype):
     return wt.to(dtype).contiguous(memory_format=torch.channels_last), F.pad(b, (0, _pad8(co) - co)).to(dtype)
 
 
+class _ConvBiasReLU(torch.autograd.Function):
+    """conv2d + bias + ReLU as cuDNN's fused forward (one pass over the output instead of three); the backward is the
+    ReLU mask followed by aten's convolution_backward (data, weight and bias gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, padding):
+        y = torch.cudnn_convolution_relu(x, w, b, [1, 1], list(padding), [1, 1], 1)
+        ctx.save_for_backward(x, w, y)
+        ctx.padding = list(padding)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, y = ctx.saved_tensors
+        g = torch.ops.aten.threshold_backward(g, y, 0)
+        gx, gw, gb = torch.ops.aten.convolution_backward(g, x, w, [w.shape[0]], [1, 1], ctx.padding, [1, 1], False, [0, 0], 1,
+                                                         [ctx.needs_input_grad[0], True, True])
+        return gx, gw, gb, None
+
+
+FUSED_CONV_RELU = True     # cuDNN fused conv + bias + ReLU forward (False: three separate passes)
+
+
 def conv_decoder(net, x):
     """ConvDecoderAE.forward (color_aggregation_network.py:51-68) of the unchanged module `net` on a channel-padded
     NHWC input x (1, 40, H, W); returns the (1, 3, H, W) residual in x's dtype."""
@@ -134,6 +157,8 @@ def conv_decoder(net, x):
     def conv(t, seq, segs, relu=True):
         c = seq if isinstance(seq, torch.nn.Conv2d) else seq[0]
         wt, b = _padded_weight(c, segs, dt)
+        if relu and FUSED_CONV_RELU:
+            return _ConvBiasReLU.apply(t, wt, b, c.padding)
         y = F.conv2d(t, wt, b, padding=c.padding)
         return F.relu(y) if relu else y
 

@@ -54,6 +54,9 @@ run("ibgs_b200 fuse_color bf16", lambda *a, **k: CA.fuse_color(*a, precision="bf
 N.lib.ibgs_profile_enable(0)
 print({k: round(v[0] / v[1], 4) for k, v in N.profile_read().items() if v[1]})
 run("ibgs_b200 fuse_color fp32", lambda *a, **k: CA.fuse_color(*a, precision="fp32", **k))
+torch.backends.cudnn.benchmark = True
+run("ibgs_b200 fuse_color bf16 + cudnn.benchmark", lambda *a, **k: CA.fuse_color(*a, precision="bf16", **k))
+run("reference fuse_color + cudnn.benchmark", CAN.fuse_color)
 from torch.profiler import profile, ProfilerActivity  # noqa: E402
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     run("profiled", lambda *a, **k: CA.fuse_color(*a, precision="bf16", **k), iters=1)

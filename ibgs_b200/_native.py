@@ -122,6 +122,8 @@ EXPORTS = [
     "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward", "ibgs_adam_step", "ibgs_set_backward_variant", "ibgs_set_forward_variant",
     "ibgs_sort_temp_bytes", "ibgs_sort_pairs", "ibgs_scan_temp_bytes", "ibgs_scan_gather",
     "ibgs_color_features_forward", "ibgs_color_features_backward",
+    "ibgs_nhwc_maxpool2_forward", "ibgs_nhwc_maxpool2_backward", "ibgs_nhwc_upsample_cat_forward",
+    "ibgs_nhwc_upsample_backward",
 ]
 
 
@@ -172,6 +174,15 @@ def _load():
     for fn in (lib.ibgs_color_features_forward, lib.ibgs_color_features_backward):
         fn.restype = C.c_int
         fn.argtypes = [C.POINTER(IbgsColorFeatArgs), C.c_void_p]
+    i32 = C.c_int32
+    lib.ibgs_nhwc_maxpool2_forward.restype = C.c_int
+    lib.ibgs_nhwc_maxpool2_forward.argtypes = [_fp, _fp, _fp, i32, i32, i32, i32, C.c_void_p]
+    lib.ibgs_nhwc_maxpool2_backward.restype = C.c_int
+    lib.ibgs_nhwc_maxpool2_backward.argtypes = [_fp, _fp, _fp, i32, i32, i32, i32, C.c_void_p]
+    lib.ibgs_nhwc_upsample_cat_forward.restype = C.c_int
+    lib.ibgs_nhwc_upsample_cat_forward.argtypes = [_fp, _fp, _fp, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]
+    lib.ibgs_nhwc_upsample_backward.restype = C.c_int
+    lib.ibgs_nhwc_upsample_backward.argtypes = [_fp, _fp, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]
     for fn in (lib.ibgs_set_backward_variant, lib.ibgs_set_forward_variant):
         fn.restype = C.c_int
         fn.argtypes = [C.c_int]

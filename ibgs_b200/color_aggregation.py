@@ -125,6 +125,89 @@ def _padded_weight(conv, in_segments, dtype):
     return wt.to(dtype).contiguous(memory_format=torch.channels_last), F.pad(b, (0, _pad8(co) - co)).to(dtype)
 
 
+def _nhwc(t):
+    """(1, C, H, W) tensor -> its (H, W, C)-contiguous storage view (copying only if it is not channels_last already)."""
+    v = t.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _fast_glue_ok(t):
+    return t.is_cuda and t.dim() == 4 and t.shape[0] == 1 and t.shape[1] % 8 == 0 and t.dtype in (torch.bfloat16, torch.float32)
+
+
+class _MaxPool2(torch.autograd.Function):
+    """nn.MaxPool2d(2) on an NHWC tensor (csrc/nhwc_ops.cu): same values and gradient routing as torch."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xv = _nhwc(x)
+        _, H, W, Cn = xv.shape
+        y = torch.empty((1, H // 2, W // 2, Cn), dtype=x.dtype, device=x.device)
+        idx = torch.empty((H // 2, W // 2, Cn), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(N.lib.ibgs_nhwc_maxpool2_forward(xv.data_ptr(), y.data_ptr(), idx.data_ptr(), H, W, Cn,
+                                                     int(x.dtype == torch.bfloat16), _stream(x.device)), "ibgs_nhwc_maxpool2_forward")
+        ctx.save_for_backward(idx)
+        ctx.shape = (H, W, Cn)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        H, W, Cn = ctx.shape
+        gv = _nhwc(g)
+        gx = torch.empty((1, H, W, Cn), dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            N.check(N.lib.ibgs_nhwc_maxpool2_backward(gv.data_ptr(), idx.data_ptr(), gx.data_ptr(), H, W, Cn,
+                                                      int(g.dtype == torch.bfloat16), _stream(g.device)), "ibgs_nhwc_maxpool2_backward")
+        return gx.permute(0, 3, 1, 2)
+
+
+class _UpsampleNearest(torch.autograd.Function):
+    """F.interpolate(x, size=(Ho, Wo), mode="nearest") on an NHWC tensor (csrc/nhwc_ops.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, Ho, Wo):
+        xv = _nhwc(x)
+        _, Hi, Wi, Cn = xv.shape
+        y = torch.empty((1, Ho, Wo, Cn), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            N.check(N.lib.ibgs_nhwc_upsample_cat_forward(xv.data_ptr(), None, y.data_ptr(), Hi, Wi, Ho, Wo, Cn, 0,
+                                                         int(x.dtype == torch.bfloat16), _stream(x.device)),
+                    "ibgs_nhwc_upsample_cat_forward")
+        ctx.shape = (Hi, Wi, Ho, Wo, Cn)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        Hi, Wi, Ho, Wo, Cn = ctx.shape
+        gv = _nhwc(g)
+        ga = torch.empty((1, Hi, Wi, Cn), dtype=g.dtype, device=g.device)
+        with torch.cuda.device(g.device):
+            N.check(N.lib.ibgs_nhwc_upsample_backward(gv.data_ptr(), ga.data_ptr(), Hi, Wi, Ho, Wo, Cn, Cn,
+                                                      int(g.dtype == torch.bfloat16), _stream(g.device)),
+                    "ibgs_nhwc_upsample_backward")
+        return ga.permute(0, 3, 1, 2), None, None
+
+
+def max_pool2(x):
+    """nn.MaxPool2d(2)(x) for a (1, C, H, W) channels_last CUDA tensor with C % 8 == 0 (bf16 / float32)."""
+    if not _fast_glue_ok(x):
+        raise RuntimeError("ibgs_b200.color_aggregation.max_pool2: (1, C % 8 == 0, H, W) CUDA bf16 / float32 tensors only")
+    return _MaxPool2.apply(x)
+
+
+def upsample_nearest(x, size):
+    """F.interpolate(x, size=size, mode="nearest") for a (1, C, H, W) channels_last CUDA tensor with C % 8 == 0."""
+    if not _fast_glue_ok(x):
+        raise RuntimeError("ibgs_b200.color_aggregation.upsample_nearest: (1, C % 8 == 0, H, W) CUDA bf16 / float32 tensors only")
+    return _UpsampleNearest.apply(x, int(size[0]), int(size[1]))
+
+
 class _ConvBiasReLU(torch.autograd.Function):
     """conv2d + bias + ReLU as cuDNN's fused forward (one pass over the output instead of three); the backward is the
     ReLU mask followed by aten's convolution_backward (data, weight and bias gradients)."""
@@ -163,14 +246,14 @@ def conv_decoder(net, x):
         return F.relu(y) if relu else y
 
     e1 = conv(x, net.enc1, [h])
-    p1 = F.max_pool2d(e1, 2)
+    p1 = max_pool2(e1)
     e2 = conv(p1, net.enc2, [h])
-    p2 = F.max_pool2d(e2, 2)
+    p2 = max_pool2(e2)
     bottleneck = conv(p2, net.enc3, [h // 2])
-    u2 = F.interpolate(bottleneck, size=e2.shape[-2:], mode="nearest")
+    u2 = upsample_nearest(bottleneck, e2.shape[-2:])
     u2 = conv(u2, net.up2_conv, [h // 4])
     d2 = conv(torch.cat([u2, e2], dim=1), net.dec2, [h // 2, h // 2])
-    u1 = F.interpolate(d2, size=e1.shape[-2:], mode="nearest")
+    u1 = upsample_nearest(d2, e1.shape[-2:])
     u1 = conv(u1, net.up1_conv, [h // 2])
     d1 = conv(torch.cat([u1, e1], dim=1), net.dec1, [h, h])
     fused = conv(torch.cat([d1, x], dim=1), net.fuse_input, [h, h])

@@ -334,6 +334,22 @@ typedef struct IbgsColorFeatArgs {
 int ibgs_color_features_forward(const IbgsColorFeatArgs* args, void* stream);
 int ibgs_color_features_backward(const IbgsColorFeatArgs* args, void* stream);
 
+/* NHWC glue of the colour network's conv decoder (ConvDecoderAE.forward, color_aggregation_network.py:51-68; optional fast
+ * path): nn.MaxPool2d(2) and F.interpolate(mode="nearest") with their backward passes on [H][W][C] tensors, C a multiple
+ * of 8, elements bf16 (bf16 != 0) or float32, 16-byte aligned.  Same results as torch (first maximum of a window wins,
+ * NaN propagates; source index = min(int(floorf(dst * (float(in) / out))), in - 1)).
+ *   maxpool2_forward:   y [H/2][W/2][C], idx [H/2][W/2][C] bytes (position 0..3 of the maximum in its window)
+ *   maxpool2_backward:  gx [H][W][C] written completely (zeros for non-maxima and the odd last row / column)
+ *   upsample_cat_forward: out [Ho][Wo][Ca+Cb] = cat(nearest-upsampled a [Hi][Wi][Ca], b [Ho][Wo][Cb]); b = NULL, Cb = 0: plain upsample
+ *   upsample_backward:  ga [Hi][Wi][Ca] = sum over the output pixels that read it of g[..][0..Ca); g has `pitch` elements per pixel */
+int ibgs_nhwc_maxpool2_forward(const void* x, void* y, uint8_t* idx, int32_t H, int32_t W, int32_t C, int32_t bf16, void* stream);
+int ibgs_nhwc_maxpool2_backward(const void* gy, const uint8_t* idx, void* gx, int32_t H, int32_t W, int32_t C, int32_t bf16,
+                                void* stream);
+int ibgs_nhwc_upsample_cat_forward(const void* a, const void* b, void* out, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo,
+                                   int32_t Ca, int32_t Cb, int32_t bf16, void* stream);
+int ibgs_nhwc_upsample_backward(const void* g, void* ga, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t Ca,
+                                int32_t pitch, int32_t bf16, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds -- cgo / JNI / ctypes on plain host arrays;
  * exercised by tests/test_gpu_host_api.py against the device entry points):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages

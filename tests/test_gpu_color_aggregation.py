@@ -140,3 +140,32 @@ def test_fast_path_argument_errors():
     with pytest.raises(RuntimeError):
         CA.color_features(pkg["warped_image"].cpu(), pkg["cam_feat"].cpu(), pkg["render"].cpu(),
                           pkg["camera_ray"].view(3, H, W).cpu(), net.per_view_mlp, 3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("H,W,C", [(2, 2, 8), (37, 53, 24), (205, 309, 16), (64, 96, 40)])
+def test_nhwc_maxpool_and_upsample_equal_torch(H, W, C, dtype):
+    """csrc/nhwc_ops.cu against torch's own max_pool2d / interpolate(nearest) on the same channels_last tensors: forward
+    bit-equal; max-pool backward bit-equal (pure routing); upsample backward equal up to one rounding of the float sum."""
+    from ibgs_b200 import color_aggregation as CA
+    g = torch.Generator().manual_seed(H * W + C)
+    x0 = torch.randn(1, C, H, W, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last)
+    x0[0, :, : H // 2, : W // 2] = x0[0, :, : H // 2, : W // 2].round()      # plenty of exact ties inside windows
+    xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+    ya, yb = CA.max_pool2(xa), torch.nn.functional.max_pool2d(xb, 2)
+    assert ya.shape == yb.shape and torch.equal(ya, yb)
+    cot = torch.randn(yb.shape, generator=g).cuda().to(dtype)
+    ya.backward(cot)
+    yb.backward(cot)
+    assert torch.equal(xa.grad, xb.grad)
+    for size in ((2 * H, 2 * W), (2 * H + 1, 2 * W + 1), (H, W), (3 * H - 1, W + 5)):
+        xa, xb = x0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        ua, ub = CA.upsample_nearest(xa, size), torch.nn.functional.interpolate(xb, size=size, mode="nearest")
+        assert ua.shape == ub.shape and torch.equal(ua, ub), size
+        cot = torch.randn(ub.shape, generator=g).cuda().to(dtype)
+        ua.backward(cot)
+        ub.backward(cot)
+        tol = 2e-2 if dtype == torch.bfloat16 else 1e-5
+        assert torch.allclose(xa.grad.float(), xb.grad.float(), rtol=tol, atol=tol), size
+    with pytest.raises(RuntimeError):
+        CA.max_pool2(torch.zeros(1, 7, 4, 4, device="cuda"))

@@ -123,7 +123,7 @@ EXPORTS = [
     "ibgs_sort_temp_bytes", "ibgs_sort_pairs", "ibgs_scan_temp_bytes", "ibgs_scan_gather",
     "ibgs_color_features_forward", "ibgs_color_features_backward",
     "ibgs_nhwc_maxpool2_forward", "ibgs_nhwc_maxpool2_backward", "ibgs_nhwc_upsample_cat_forward",
-    "ibgs_nhwc_upsample_backward",
+    "ibgs_nhwc_upsample_backward", "ibgs_nhwc_relu_bias_backward",
 ]
 
 
@@ -183,6 +183,8 @@ def _load():
     lib.ibgs_nhwc_upsample_cat_forward.argtypes = [_fp, _fp, _fp, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]
     lib.ibgs_nhwc_upsample_backward.restype = C.c_int
     lib.ibgs_nhwc_upsample_backward.argtypes = [_fp, _fp, i32, i32, i32, i32, i32, i32, i32, C.c_void_p]
+    lib.ibgs_nhwc_relu_bias_backward.restype = C.c_int
+    lib.ibgs_nhwc_relu_bias_backward.argtypes = [_fp, i32, _fp, _fp, _fp, C.c_int64, i32, i32, C.c_void_p]
     for fn in (lib.ibgs_set_backward_variant, lib.ibgs_set_forward_variant):
         fn.restype = C.c_int
         fn.argtypes = [C.c_int]

@@ -222,10 +222,54 @@ class _ConvBiasReLU(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, w, y = ctx.saved_tensors
-        g = torch.ops.aten.threshold_backward(g, y, 0)
-        gx, gw, gb = torch.ops.aten.convolution_backward(g, x, w, [w.shape[0]], [1, 1], ctx.padding, [1, 1], False, [0, 0], 1,
-                                                         [ctx.needs_input_grad[0], True, True])
-        return gx, gw, gb, None
+        # ReLU mask + bias gradient in one pass (csrc/nhwc_ops.cu); g is read in place even when it is a channel slice of
+        # a concatenation's gradient (pitch = channels of the wider buffer)
+        _, Cn, H, W = y.shape
+        gv = g.permute(0, 2, 3, 1)
+        st = gv.stride()
+        sliced = (g.dtype == y.dtype and st[3] == 1 and st[2] % 8 == 0 and st[2] >= Cn and st[1] == W * st[2]
+                  and g.data_ptr() % 16 == 0)
+        if not sliced:
+            gv = gv.to(y.dtype).contiguous()
+            st = gv.stride()
+        yv = _nhwc(y)
+        gm = torch.empty((1, H, W, Cn), dtype=y.dtype, device=y.device)
+        db = torch.zeros(Cn, dtype=torch.float32, device=y.device)
+        with torch.cuda.device(y.device):
+            N.check(N.lib.ibgs_nhwc_relu_bias_backward(gv.data_ptr(), st[2], yv.data_ptr(), gm.data_ptr(), db.data_ptr(),
+                                                       H * W, Cn, int(y.dtype == torch.bfloat16), _stream(y.device)),
+                    "ibgs_nhwc_relu_bias_backward")
+        gx, gw, _ = torch.ops.aten.convolution_backward(gm.permute(0, 3, 1, 2), x, w, None, [1, 1], ctx.padding, [1, 1], False,
+                                                        [0, 0], 1, [ctx.needs_input_grad[0], True, False])
+        return gx, gw, db.to(w.dtype), None
+
+
+class _Cat2(torch.autograd.Function):
+    """torch.cat([a, b], dim=1) of two (1, C, H, W) NHWC tensors in one pass at copy rate (csrc/nhwc_ops.cu, identity
+    mapping of the upsample+cat kernel); the backward hands out the two channel slices as views, like torch."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        av, bv = _nhwc(a), _nhwc(b)
+        _, H, W, Ca = av.shape
+        Cb = bv.shape[3]
+        out = torch.empty((1, H, W, Ca + Cb), dtype=a.dtype, device=a.device)
+        with torch.cuda.device(a.device):
+            N.check(N.lib.ibgs_nhwc_upsample_cat_forward(av.data_ptr(), bv.data_ptr(), out.data_ptr(), H, W, H, W, Ca, Cb,
+                                                         int(a.dtype == torch.bfloat16), _stream(a.device)),
+                    "ibgs_nhwc_upsample_cat_forward")
+        ctx.ca = Ca
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, :ctx.ca], g[:, ctx.ca:]
+
+
+def cat2(a, b):
+    if not (_fast_glue_ok(a) and _fast_glue_ok(b) and a.dtype == b.dtype and a.shape[2:] == b.shape[2:]):
+        raise RuntimeError("ibgs_b200.color_aggregation.cat2: two (1, C % 8 == 0, H, W) CUDA tensors of one dtype and size")
+    return _Cat2.apply(a, b)
 
 
 FUSED_CONV_RELU = True     # cuDNN fused conv + bias + ReLU forward (False: three separate passes)
@@ -252,11 +296,11 @@ def conv_decoder(net, x):
     bottleneck = conv(p2, net.enc3, [h // 2])
     u2 = upsample_nearest(bottleneck, e2.shape[-2:])
     u2 = conv(u2, net.up2_conv, [h // 4])
-    d2 = conv(torch.cat([u2, e2], dim=1), net.dec2, [h // 2, h // 2])
+    d2 = conv(cat2(u2, e2), net.dec2, [h // 2, h // 2])
     u1 = upsample_nearest(d2, e1.shape[-2:])
     u1 = conv(u1, net.up1_conv, [h // 2])
-    d1 = conv(torch.cat([u1, e1], dim=1), net.dec1, [h, h])
-    fused = conv(torch.cat([d1, x], dim=1), net.fuse_input, [h, h])
+    d1 = conv(cat2(u1, e1), net.dec1, [h, h])
+    fused = conv(cat2(d1, x), net.fuse_input, [h, h])
     return conv(fused, net.final, [h], relu=False)[:, :3]
 
 

@@ -1,6 +1,6 @@
 // nhwc_ops.cu -- the memory-bound glue between the conv decoder's convolutions, on the NHWC
-// layout color_features.cu produces: 2x2 max pooling and nearest-neighbour upsampling fused with the channel
-// concatenation that follows it, forward and backward, bf16 or float32.
+// layout color_features.cu produces: 2x2 max pooling, nearest-neighbour upsampling, channel concatenation and the ReLU
+// backward fused with the bias gradient, bf16 or float32.
 //
 // Reference behaviour (ConvDecoderAE.forward, color_aggregation_network.py:51-68, through torch):
 //   p = nn.MaxPool2d(2)(e)                          kernel 2, stride 2, no padding, floor: out = in // 2; the FIRST maximum
@@ -8,8 +8,9 @@
 //   u = F.interpolate(b, size=e.shape[-2:], mode="nearest"); torch.cat([conv(u), e], 1)
 //                                                   source index = min(int(floorf(dst * (float(in) / out))), in - 1)
 // torch's generic NHWC kernels for these run far below the copy rate (max_pool_backward_nhwc 0.17 ms for 80 MB in + out,
-// upsample 0.08 ms, the cat that follows another 0.12 ms).  Here every thread moves 16-byte channel groups and the
-// upsampled tensor is never materialised on its own: it is written straight into its half of the concatenated buffer.
+// upsample 0.08 ms, a cat 0.12 ms, threshold_backward on the channel-sliced gradient of a cat 0.11 ms).  Here every
+// thread moves 16-byte channel groups; one kernel serves the upsample (b = NULL), the concatenation (identity mapping) and
+// both at once; sliced gradients are read in place through a pitch.
 //
 // All tensors are [H][W][C] with C a multiple of 8 elements; `pitch` arguments are in elements (a channel slice of a wider
 // NHWC buffer is addressed by base pointer + pitch).
@@ -181,6 +182,42 @@ __global__ void __launch_bounds__(256) upsample_backward_kernel(const T* __restr
   }
 }
 
+// ---- ReLU backward fused with the bias gradient ---------------------------------------------------------------------------
+// gm[p][c] = y[p][c] > 0 ? g[p * pitch + c] : 0  (aten::threshold_backward on a possibly channel-sliced gradient) and
+// db[c] += sum_p gm[p][c] (the bias gradient aten::convolution_backward would reduce in another pass).
+// blockDim.x = G * k threads (G = channel groups per pixel): thread t always owns group t % G, so its channel sums stay in
+// registers over the grid-stride loop; one shared-memory reduction and one global atomic per (block, channel) at the end.
+template <typename T>
+__global__ void __launch_bounds__(256) relu_bias_backward_kernel(const T* __restrict__ g, int pitch, const T* __restrict__ y,
+                                                                 T* __restrict__ gm, float* __restrict__ db, long long npix,
+                                                                 int C) {
+  constexpr int VN = Vec<T>::N;
+  extern __shared__ float s_db[];
+  const int G = C / VN;
+  const int gq = threadIdx.x % G, lp = threadIdx.x / G, ppb = blockDim.x / G;   // pixels per block and step
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_db[c] = 0.f;
+  __syncthreads();
+  float acc[VN];
+#pragma unroll
+  for (int k = 0; k < VN; k++) acc[k] = 0.f;
+  for (long long p = (long long)blockIdx.x * ppb + lp; p < npix; p += (long long)gridDim.x * ppb) {
+    const Vec<T> gv = ld16(g + (size_t)p * pitch + gq * VN);
+    const Vec<T> yv = ld16(y + (size_t)p * C + gq * VN);
+    Vec<T> o;
+#pragma unroll
+    for (int k = 0; k < VN; k++) {
+      const bool on = to_f(yv.v[k]) > 0.f;
+      o.v[k] = on ? gv.v[k] : from_f<T>(0.f);
+      acc[k] += on ? to_f(gv.v[k]) : 0.f;
+    }
+    st16(gm + (size_t)p * C + gq * VN, o);
+  }
+#pragma unroll
+  for (int k = 0; k < VN; k++) atomicAdd(&s_db[gq * VN + k], acc[k]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(db + c, s_db[c]);
+}
+
 int grid_for(long long total) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -271,6 +308,32 @@ extern "C" int ibgs_nhwc_upsample_backward(const void* g, void* ga, int32_t Hi, 
     const long long total = (long long)Hi * Wi * (Ca / 4);
     upsample_backward_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)g, (float*)ga, Hi, Wi, Ho, Wo, Ca, pitch, sh, sw);
   }
+  KERNEL_CHECK(0, s);
+  return IBGS_OK;
+}
+
+extern "C" int ibgs_nhwc_relu_bias_backward(const void* g, int32_t pitch, const void* y, void* gm, float* db, int64_t npix,
+                                            int32_t C, int32_t bf16, void* stream_v) {
+  cudaStream_t s = (cudaStream_t)stream_v;
+  if (npix < 0 || C <= 0 || C % 8 || pitch < C || pitch % 8 || C > 2048) {
+    ibgs_set_error("bad relu_bias_backward shape: npix %lld, C %d, pitch %d", (long long)npix, C, pitch);
+    return IBGS_EINVAL;
+  }
+  if (npix == 0) return IBGS_OK;
+  if (!g || !y || !gm || !db || (((uintptr_t)g | (uintptr_t)y | (uintptr_t)gm) % 16)) {
+    ibgs_set_error("relu_bias_backward: null or misaligned pointer");
+    return IBGS_EINVAL;
+  }
+  const int VN = bf16 ? 8 : 4, G = C / VN;
+  const int threads = G * std::max(1, 256 / G);
+  const int ppb = threads / G;
+  const int blocks = grid_for(((npix + ppb - 1) / ppb) * 256) ;
+  if (bf16)
+    relu_bias_backward_kernel<__nv_bfloat16><<<blocks, threads, C * sizeof(float), s>>>((const __nv_bfloat16*)g, pitch, (const __nv_bfloat16*)y,
+                                                                                     (__nv_bfloat16*)gm, db, npix, C);
+  else
+    relu_bias_backward_kernel<float><<<blocks, threads, C * sizeof(float), s>>>((const float*)g, pitch, (const float*)y, (float*)gm, db,
+                                                                               npix, C);
   KERNEL_CHECK(0, s);
   return IBGS_OK;
 }

@@ -349,6 +349,11 @@ int ibgs_nhwc_upsample_cat_forward(const void* a, const void* b, void* out, int3
                                    int32_t Ca, int32_t Cb, int32_t bf16, void* stream);
 int ibgs_nhwc_upsample_backward(const void* g, void* ga, int32_t Hi, int32_t Wi, int32_t Ho, int32_t Wo, int32_t Ca,
                                 int32_t pitch, int32_t bf16, void* stream);
+/* ReLU backward of a conv + bias + ReLU layer fused with the bias gradient: gm[p][c] = y[p][c] > 0 ? g[p*pitch + c] : 0
+ * (aten::threshold_backward; g may be a channel slice of a wider NHWC gradient: `pitch` elements per pixel) and
+ * db[c] += sum_p gm[p][c] (float32, ACCUMULATED: the caller zeroes it). */
+int ibgs_nhwc_relu_bias_backward(const void* g, int32_t pitch, const void* y, void* gm, float* db, int64_t npix, int32_t C,
+                                 int32_t bf16, void* stream);
 
 /* Host-buffer convenience entry points (what a non-torch caller binds -- cgo / JNI / ctypes on plain host arrays;
  * exercised by tests/test_gpu_host_api.py against the device entry points):

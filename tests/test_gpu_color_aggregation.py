@@ -169,3 +169,35 @@ def test_nhwc_maxpool_and_upsample_equal_torch(H, W, C, dtype):
         assert torch.allclose(xa.grad.float(), xb.grad.float(), rtol=tol, atol=tol), size
     with pytest.raises(RuntimeError):
         CA.max_pool2(torch.zeros(1, 7, 4, 4, device="cuda"))
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_cat_and_fused_conv_relu_layer_equal_torch(dtype):
+    """cat2 (copy-rate concatenation) and the conv + bias + ReLU layer whose backward runs the fused ReLU-mask / bias-gradient
+    kernel on a channel-SLICED incoming gradient, against the same layers written with torch ops."""
+    from ibgs_b200 import color_aggregation as CA
+    g = torch.Generator().manual_seed(7)
+    H, W, Ca, Cb = 45, 67, 24, 16
+    mk = lambda c: torch.randn(1, c, H, W, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last)
+    a0, b0 = mk(Ca), mk(Cb)
+    wa = (torch.randn(Ca, Ca, 3, 3, generator=g) * 0.1).cuda().to(dtype).contiguous(memory_format=torch.channels_last)
+    ba = torch.randn(Ca, generator=g).cuda().to(dtype)
+    cot = torch.randn(1, Ca + Cb, H, W, generator=g).cuda().to(dtype).contiguous(memory_format=torch.channels_last)
+    res = []
+    for fast in (True, False):
+        a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        w_, b_ = wa.clone().requires_grad_(True), ba.clone().requires_grad_(True)
+        if fast:
+            y = CA._ConvBiasReLU.apply(a, w_, b_, (1, 1))
+            out = CA.cat2(y, b)
+        else:
+            y = torch.relu(torch.nn.functional.conv2d(a, w_, b_, padding=1))
+            out = torch.cat([y, b], 1)
+        out.backward(cot)          # y receives a channel slice of `cot`
+        res.append((out.detach(), a.grad, b.grad, w_.grad, b_.grad))
+    tol = dict(rtol=3e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=2e-3, atol=2e-3)   # tf32 / bf16 convolutions
+    assert torch.allclose(res[0][0].float(), res[1][0].float(), **tol)
+    assert torch.equal(res[0][2], res[1][2])                                   # gradient of the second cat operand: a pure slice
+    for i in (1, 3, 4):
+        # bf16: the fused forward rounds once after bias + ReLU, the unfused one after each op -> a few ReLU masks flip
+        assert _rel(res[0][i], res[1][i]) <= (8e-2 if dtype == torch.bfloat16 else 3e-3), (i, _rel(res[0][i], res[1][i]))

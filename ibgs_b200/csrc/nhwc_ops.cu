@@ -187,6 +187,9 @@ __global__ void __launch_bounds__(256) upsample_backward_kernel(const T* __restr
 // db[c] += sum_p gm[p][c] (the bias gradient aten::convolution_backward would reduce in another pass).
 // blockDim.x = G * k threads (G = channel groups per pixel): thread t always owns group t % G, so its channel sums stay in
 // registers over the grid-stride loop; one shared-memory reduction and one global atomic per (block, channel) at the end.
+#ifndef RELU_UNROLL
+#define RELU_UNROLL 1
+#endif
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bias_backward_kernel(const T* __restrict__ g, int pitch, const T* __restrict__ y,
                                                                  T* __restrict__ gm, float* __restrict__ db, long long npix,
@@ -200,17 +203,32 @@ __global__ void __launch_bounds__(256) relu_bias_backward_kernel(const T* __rest
   float acc[VN];
 #pragma unroll
   for (int k = 0; k < VN; k++) acc[k] = 0.f;
-  for (long long p = (long long)blockIdx.x * ppb + lp; p < npix; p += (long long)gridDim.x * ppb) {
-    const Vec<T> gv = ld16(g + (size_t)p * pitch + gq * VN);
-    const Vec<T> yv = ld16(y + (size_t)p * C + gq * VN);
-    Vec<T> o;
+  // RELU_UNROLL pixels per trip: that many pairs of independent 16-byte loads in flight per thread
+  const long long step = (long long)gridDim.x * ppb;
+  for (long long p0 = (long long)blockIdx.x * ppb + lp; p0 < npix; p0 += RELU_UNROLL * step) {
+    Vec<T> gv[RELU_UNROLL], yv[RELU_UNROLL];
 #pragma unroll
-    for (int k = 0; k < VN; k++) {
-      const bool on = to_f(yv.v[k]) > 0.f;
-      o.v[k] = on ? gv.v[k] : from_f<T>(0.f);
-      acc[k] += on ? to_f(gv.v[k]) : 0.f;
+    for (int u = 0; u < RELU_UNROLL; u++) {
+      const long long p = p0 + u * step;
+      if (p < npix) {
+        gv[u] = ld16(g + (size_t)p * pitch + gq * VN);
+        yv[u] = ld16(y + (size_t)p * C + gq * VN);
+      }
     }
-    st16(gm + (size_t)p * C + gq * VN, o);
+#pragma unroll
+    for (int u = 0; u < RELU_UNROLL; u++) {
+      const long long p = p0 + u * step;
+      if (p < npix) {
+        Vec<T> o;
+#pragma unroll
+        for (int k = 0; k < VN; k++) {
+          const bool on = to_f(yv[u].v[k]) > 0.f;
+          o.v[k] = on ? gv[u].v[k] : from_f<T>(0.f);
+          acc[k] += on ? to_f(gv[u].v[k]) : 0.f;
+        }
+        st16(gm + (size_t)p * C + gq * VN, o);
+      }
+    }
   }
 #pragma unroll
   for (int k = 0; k < VN; k++) atomicAdd(&s_db[gq * VN + k], acc[k]);

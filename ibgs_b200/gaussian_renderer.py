@@ -14,8 +14,8 @@ this module is what a caller switches to when it also wants the Python prologue 
     backward kernel itself (`accumulate_grads`) instead of through a temporary + autograd's add pass;
   * with do_render_src_depth the source-view depths are rendered by ONE batched depth-only pass
     (ibgs_b200.depth_batch.render_depth_views) instead of one rasterizer call per source view (:245-252);
-  * the depth-to-normal map (utils/graphics_utils.py:38-75 through render_normal, :15-26) is evaluated from the pinhole
-    model directly (4 shifted differences, one cross product) instead of through the NDC round trip.
+  * the depth-to-normal map (utils/graphics_utils.py:38-75 through render_normal, :15-26) is one CUDA kernel per direction
+    (csrc/depth_normal.cu) instead of ~12 + ~25 elementwise torch kernels.
 
 Python-side SH / covariance evaluation (pipe.convert_SHs_python, pipe.compute_cov3D_python) is not covered:
 NotImplementedError (those flags exist to bypass the CUDA path).  There is no CPU path.
@@ -24,9 +24,12 @@ import math
 import random
 from typing import Optional
 
+import ctypes as C
+
 import numpy as np
 import torch
 
+from . import _native as N
 from . import fused
 from .depth_batch import render_depth_views
 from .diff_plane_rasterization import GaussianRasterizationSettings, GaussianRasterizer
@@ -92,22 +95,54 @@ def _closest_frames(viewpoint_camera, scene, args):
     return np.array(order)
 
 
+class _DepthNormal(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, fx, fy, cx, cy):
+        if not depth.is_cuda:
+            raise RuntimeError("ibgs_b200.gaussian_renderer: tensors must be CUDA tensors (there is no CPU path)")
+        d = depth.detach().float().contiguous()
+        H, W = d.shape
+        out = torch.empty((3, H, W), dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            N.check(N.lib.ibgs_depth_normal_forward(d.data_ptr(), out.data_ptr(), H, W, fx, fy, cx, cy,
+                                                    C.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)),
+                    "ibgs_depth_normal_forward")
+        ctx.save_for_backward(d)
+        ctx.k = (fx, fy, cx, cy)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        H, W = d.shape
+        g = g.detach().float().contiguous()
+        gd = torch.empty_like(d)
+        with torch.cuda.device(d.device):
+            N.check(N.lib.ibgs_depth_normal_backward(d.data_ptr(), g.data_ptr(), gd.data_ptr(), H, W, *ctx.k,
+                                                     C.c_void_p(torch.cuda.current_stream(d.device).cuda_stream)),
+                    "ibgs_depth_normal_backward")
+        return gd, None, None, None, None
+
+
 def depth_normal(viewpoint_cam, depth):
     """Unit normal map (3, H, W) of a depth image (H, W): render_normal (gaussian_renderer/__init__.py:15-26) followed by
-    the renormalisation of :332-335.  Points are back-projected with the pinhole intrinsics of
-    Camera.get_calib_matrix_nerf (scene/cameras.py:115-118); the normal is the cross product of the horizontal and
-    vertical central differences (utils/graphics_utils.py:65-72), zero on the 1-pixel border."""
+    the renormalisation of :332-335, one CUDA kernel per direction (csrc/depth_normal.cu).  Points are back-projected with
+    the pinhole intrinsics of Camera.get_calib_matrix_nerf (scene/cameras.py:115-118); the normal is the cross product of
+    the horizontal and vertical central differences (utils/graphics_utils.py:65-72), zero on the 1-pixel border."""
+    return _DepthNormal.apply(depth, float(viewpoint_cam.Fx), float(viewpoint_cam.Fy), float(viewpoint_cam.Cx),
+                              float(viewpoint_cam.Cy))
+
+
+def depth_normal_torch(viewpoint_cam, depth):
+    """The same map written with torch ops (what the kernel is tested against; not used by render())."""
     H, W = depth.shape
     fx, fy, cx, cy = float(viewpoint_cam.Fx), float(viewpoint_cam.Fy), float(viewpoint_cam.Cx), float(viewpoint_cam.Cy)
     xs = (torch.arange(W, device=depth.device, dtype=depth.dtype) - cx) / fx
     ys = (torch.arange(H, device=depth.device, dtype=depth.dtype) - cy) / fy
-    X = depth * xs[None, :]
-    Y = depth * ys[:, None]
-    pts = torch.stack((X, Y, depth), 0)                                  # (3, H, W)
+    pts = torch.stack((depth * xs[None, :], depth * ys[:, None], depth), 0)                                  # (3, H, W)
     l2r = pts[:, 1:H - 1, 2:W] - pts[:, 1:H - 1, 0:W - 2]
     b2t = pts[:, 0:H - 2, 1:W - 1] - pts[:, 2:H, 1:W - 1]
-    n = torch.cross(l2r, b2t, dim=0)
-    n = torch.nn.functional.normalize(n, p=2, dim=0)
+    n = torch.nn.functional.normalize(torch.cross(l2r, b2t, dim=0), p=2, dim=0)
     n = torch.nn.functional.pad(n, (1, 1, 1, 1), mode="constant")
     return n / (torch.norm(n, dim=0, keepdim=True) + 1e-8)
 

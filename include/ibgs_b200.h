@@ -355,6 +355,14 @@ int ibgs_nhwc_upsample_backward(const void* g, void* ga, int32_t Hi, int32_t Wi,
 int ibgs_nhwc_relu_bias_backward(const void* g, int32_t pitch, const void* y, void* gm, float* db, int64_t npix, int32_t C,
                                  int32_t bf16, void* stream);
 
+/* Unit normal map of a depth image (optional fast path): render_normal + the renormalisation of
+ * gaussian_renderer/__init__.py:15-26,332-335 (utils/graphics_utils.py:38-75 with Camera.get_calib_matrix_nerf's pinhole
+ * intrinsics): normal [3][H][W] from depth [H][W], zero on the 1-pixel border; the backward writes g_depth [H][W]. */
+int ibgs_depth_normal_forward(const float* depth, float* normal, int32_t H, int32_t W, float fx, float fy, float cx, float cy,
+                              void* stream);
+int ibgs_depth_normal_backward(const float* depth, const float* g_normal, float* g_depth, int32_t H, int32_t W, float fx,
+                               float fy, float cx, float cy, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds -- cgo / JNI / ctypes on plain host arrays;
  * exercised by tests/test_gpu_host_api.py against the device entry points):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages

@@ -110,3 +110,23 @@ def test_fast_train_iteration_equals_unchanged_glue(exposure, precision):
         assert U.rel_l2(g1[n], g0[n]) <= gtol, (n, U.rel_l2(g1[n], g0[n]))
     for a, b in zip(n1, n0):
         assert U.rel_l2(a, b) <= gtol, U.rel_l2(a, b)
+
+
+@pytest.mark.parametrize("H,W", [(3, 3), (37, 53), (240, 321)])
+def test_depth_normal_kernel_equals_torch_expressions(H, W):
+    """csrc/depth_normal.cu against the same map written with torch ops (and through them against the reference's
+    render_normal, compared in test_fast_render_equals_unchanged_render): values and the depth gradient."""
+    import types
+    import ibgs_b200.gaussian_renderer as FR
+    cam = types.SimpleNamespace(Fx=310.5, Fy=305.25, Cx=W / 2 - 0.3, Cy=H / 2 + 0.4)
+    g = torch.Generator().manual_seed(H + W)
+    d0 = (2.0 + torch.rand(H, W, generator=g) + 0.2 * torch.randn(H, W, generator=g).cumsum(1) / W).cuda()
+    d0[H // 2:H // 2 + 2, W // 2:W // 2 + 2] = 3.0          # a flat patch: zero cross products, the eps branches
+    da, db = d0.clone().requires_grad_(True), d0.clone().requires_grad_(True)
+    na, nb = FR.depth_normal(cam, da), FR.depth_normal_torch(cam, db)
+    assert na.shape == (3, H, W) and (na - nb).abs().max().item() <= 3e-5   # differences of nearby depths cancel
+    assert not na[:, 0].any() and not na[:, -1].any() and not na[:, :, 0].any() and not na[:, :, -1].any()
+    cot = torch.randn(3, H, W, generator=g).cuda()
+    na.backward(cot)
+    nb.backward(cot)
+    assert U.rel_l2(da.grad, db.grad) <= 1e-4, U.rel_l2(da.grad, db.grad)

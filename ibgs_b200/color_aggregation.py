@@ -10,8 +10,8 @@ the leaves the caller's optimizer updates.  What changes is how the numbers are 
     (:121-131) are ONE hand-written CUDA kernel per direction (csrc/color_features.cu through the C ABI), writing the
     decoder's input directly as NHWC with 40 channels (38 + 2 zero), bf16 when `precision="bf16"`;
   * the conv decoder (ConvDecoderAE, :6-68) runs through cuDNN on that layout with every channel count rounded up to a
-    multiple of 8 (38 -> 40, 19 -> 24, 9 -> 16): zero-padded weights rebuilt from the module's parameters inside the
-    graph, so gradients reach the unpadded parameters.  The reference's shapes (38 / 19 / 9 / 76 channels, NCHW fp32) do
+    multiple of 8 (38 -> 40, 19 -> 24, 9 -> 16): zero-padded copies of the module's weights made inside each layer's
+    autograd function, whose backward un-pads the weight gradient again, so gradients reach the unpadded parameters.  The reference's shapes (38 / 19 / 9 / 76 channels, NCHW fp32) do
     not meet the tensor-core kernels' alignment and run on SIMT / tf32 implicit-GEMM fall-backs: 10.0 ms forward+backward
     at 1237x822; padded NHWC bf16: 6.3 ms, fp32 (tf32) 6.7 ms (tools/colornet_bench.py, profiles/NOTES.md);
   * the exposure affine (:136-153) solves the same least-squares problem through its 4x4 normal equations in float64
@@ -111,20 +111,6 @@ def _pad8(c):
     return (c + 7) // 8 * 8
 
 
-def _padded_weight(conv, in_segments, dtype):
-    """conv.weight / bias with the output channels and every input segment zero-padded to a multiple of 8 channels
-    (`in_segments`: the channel counts of the tensors that were concatenated to form this conv's input)."""
-    wt, b = conv.weight, conv.bias
-    co = wt.shape[0]
-    parts, at = [], 0
-    for c in in_segments:
-        parts.append(F.pad(wt[:, at:at + c], (0, 0, 0, 0, 0, _pad8(c) - c)))
-        at += c
-    wt = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
-    wt = F.pad(wt, (0, 0, 0, 0, 0, 0, 0, _pad8(co) - co))
-    return wt.to(dtype).contiguous(memory_format=torch.channels_last), F.pad(b, (0, _pad8(co) - co)).to(dtype)
-
-
 def _nhwc(t):
     """(1, C, H, W) tensor -> its (H, W, C)-contiguous storage view (copying only if it is not channels_last already)."""
     v = t.permute(0, 2, 3, 1)
@@ -208,40 +194,79 @@ def upsample_nearest(x, size):
     return _UpsampleNearest.apply(x, int(size[0]), int(size[1]))
 
 
-class _ConvBiasReLU(torch.autograd.Function):
-    """conv2d + bias + ReLU as cuDNN's fused forward (one pass over the output instead of three); the backward is the
-    ReLU mask followed by aten's convolution_backward (data, weight and bias gradients)."""
+def _pad_wb(w, b, segs, dtype):
+    """Zero-padded copies (no autograd graph) of a conv's weight / bias: output channels and every input segment rounded up
+    to a multiple of 8 channels, weight in channels_last, both in `dtype`."""
+    co, _, kh, kw = w.shape
+    cop, cip = _pad8(co), sum(_pad8(c) for c in segs)
+    wp = torch.zeros((cop, cip, kh, kw), dtype=dtype, device=w.device).contiguous(memory_format=torch.channels_last)
+    at = atp = 0
+    for c in segs:
+        wp[:co, atp:atp + c].copy_(w[:, at:at + c])
+        at += c
+        atp += _pad8(c)
+    bp = torch.zeros(cop, dtype=dtype, device=w.device)
+    bp[:co].copy_(b)
+    return wp, bp
+
+
+def _unpad_w(gwp, co, segs, dtype):
+    parts, atp = [], 0
+    for c in segs:
+        parts.append(gwp[:co, atp:atp + c])
+        atp += _pad8(c)
+    g = parts[0] if len(parts) == 1 else torch.cat(parts, 1)
+    return g.to(dtype).contiguous()
+
+
+class _ConvLayer(torch.autograd.Function):
+    """One conv (+ bias) (+ ReLU) layer of the decoder on channel-padded NHWC activations, taking the module's UNPADDED
+    weight / bias: the padding is done inside (a handful of copies, no autograd nodes), the forward is cuDNN's fused
+    conv + bias + ReLU (or conv + bias), the backward is this repo's ReLU-mask + bias-gradient kernel followed by aten's
+    convolution_backward for the data and weight gradients, un-padded again before they are returned."""
 
     @staticmethod
-    def forward(ctx, x, w, b, padding):
-        y = torch.cudnn_convolution_relu(x, w, b, [1, 1], list(padding), [1, 1], 1)
-        ctx.save_for_backward(x, w, y)
-        ctx.padding = list(padding)
+    def forward(ctx, x, w, b, segs, padding, relu):
+        wp, bp = _pad_wb(w, b, segs, x.dtype)
+        padding = list(padding)
+        if relu:
+            y = torch.cudnn_convolution_relu(x, wp, bp, [1, 1], padding, [1, 1], 1)
+            ctx.save_for_backward(x, wp, y)
+        else:
+            y = F.conv2d(x, wp, bp, padding=padding)
+            ctx.save_for_backward(x, wp)
+        ctx.cfg = (tuple(segs), padding, bool(relu), w.shape[0], w.dtype, b.dtype)
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, w, y = ctx.saved_tensors
-        # ReLU mask + bias gradient in one pass (csrc/nhwc_ops.cu); g is read in place even when it is a channel slice of
-        # a concatenation's gradient (pitch = channels of the wider buffer)
-        _, Cn, H, W = y.shape
-        gv = g.permute(0, 2, 3, 1)
-        st = gv.stride()
-        sliced = (g.dtype == y.dtype and st[3] == 1 and st[2] % 8 == 0 and st[2] >= Cn and st[1] == W * st[2]
-                  and g.data_ptr() % 16 == 0)
-        if not sliced:
-            gv = gv.to(y.dtype).contiguous()
+        segs, padding, relu, co, wdt, bdt = ctx.cfg
+        if relu:
+            x, wp, y = ctx.saved_tensors
+            # ReLU mask + bias gradient in one pass (csrc/nhwc_ops.cu); g is read in place even when it is a channel slice
+            # of a concatenation's gradient (pitch = channels of the wider buffer)
+            _, Cn, H, W = y.shape
+            gv = g.permute(0, 2, 3, 1)
             st = gv.stride()
-        yv = _nhwc(y)
-        gm = torch.empty((1, H, W, Cn), dtype=y.dtype, device=y.device)
-        db = torch.zeros(Cn, dtype=torch.float32, device=y.device)
-        with torch.cuda.device(y.device):
-            N.check(N.lib.ibgs_nhwc_relu_bias_backward(gv.data_ptr(), st[2], yv.data_ptr(), gm.data_ptr(), db.data_ptr(),
-                                                       H * W, Cn, int(y.dtype == torch.bfloat16), _stream(y.device)),
-                    "ibgs_nhwc_relu_bias_backward")
-        gx, gw, _ = torch.ops.aten.convolution_backward(gm.permute(0, 3, 1, 2), x, w, None, [1, 1], ctx.padding, [1, 1], False,
-                                                        [0, 0], 1, [ctx.needs_input_grad[0], True, False])
-        return gx, gw, db.to(w.dtype), None
+            sliced = (g.dtype == y.dtype and st[3] == 1 and st[2] % 8 == 0 and st[2] >= Cn and st[1] == W * st[2]
+                      and g.data_ptr() % 16 == 0)
+            if not sliced:
+                gv = gv.to(y.dtype).contiguous()
+                st = gv.stride()
+            yv = _nhwc(y)
+            gm = torch.empty((1, H, W, Cn), dtype=y.dtype, device=y.device)
+            db = torch.zeros(Cn, dtype=torch.float32, device=y.device)
+            with torch.cuda.device(y.device):
+                N.check(N.lib.ibgs_nhwc_relu_bias_backward(gv.data_ptr(), st[2], yv.data_ptr(), gm.data_ptr(), db.data_ptr(),
+                                                           H * W, Cn, int(y.dtype == torch.bfloat16), _stream(y.device)),
+                        "ibgs_nhwc_relu_bias_backward")
+            gx, gwp, _ = torch.ops.aten.convolution_backward(gm.permute(0, 3, 1, 2), x, wp, None, [1, 1], padding, [1, 1], False,
+                                                             [0, 0], 1, [ctx.needs_input_grad[0], True, False])
+        else:
+            x, wp = ctx.saved_tensors
+            gx, gwp, db = torch.ops.aten.convolution_backward(g.to(x.dtype), x, wp, [wp.shape[0]], [1, 1], padding, [1, 1], False,
+                                                              [0, 0], 1, [ctx.needs_input_grad[0], True, True])
+        return gx, _unpad_w(gwp, co, segs, wdt), db[:co].to(bdt), None, None, None
 
 
 class _Cat2(torch.autograd.Function):
@@ -272,22 +297,13 @@ def cat2(a, b):
     return _Cat2.apply(a, b)
 
 
-FUSED_CONV_RELU = True     # cuDNN fused conv + bias + ReLU forward (False: three separate passes)
-
-
 def conv_decoder(net, x):
     """ConvDecoderAE.forward (color_aggregation_network.py:51-68) of the unchanged module `net` on a channel-padded
     NHWC input x (1, 40, H, W); returns the (1, 3, H, W) residual in x's dtype."""
     h = net.enc1[0].in_channels
-    dt = x.dtype
-
     def conv(t, seq, segs, relu=True):
         c = seq if isinstance(seq, torch.nn.Conv2d) else seq[0]
-        wt, b = _padded_weight(c, segs, dt)
-        if relu and FUSED_CONV_RELU:
-            return _ConvBiasReLU.apply(t, wt, b, c.padding)
-        y = F.conv2d(t, wt, b, padding=c.padding)
-        return F.relu(y) if relu else y
+        return _ConvLayer.apply(t, c.weight, c.bias, tuple(segs), tuple(c.padding), relu)
 
     e1 = conv(x, net.enc1, [h])
     p1 = max_pool2(e1)

@@ -188,7 +188,7 @@ def test_cat_and_fused_conv_relu_layer_equal_torch(dtype):
         a, b = a0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
         w_, b_ = wa.clone().requires_grad_(True), ba.clone().requires_grad_(True)
         if fast:
-            y = CA._ConvBiasReLU.apply(a, w_, b_, (1, 1))
+            y = CA._ConvLayer.apply(a, w_, b_, (Ca,), (1, 1), True)
             out = CA.cat2(y, b)
         else:
             y = torch.relu(torch.nn.functional.conv2d(a, w_, b_, padding=1))

@@ -14,6 +14,8 @@ this module is what a caller switches to when it also wants the Python prologue 
     backward kernel itself (`accumulate_grads`) instead of through a temporary + autograd's add pass;
   * with do_render_src_depth the source-view depths are rendered by ONE batched depth-only pass
     (ibgs_b200.depth_batch.render_depth_views) instead of one rasterizer call per source view (:245-252);
+  * the two torch.inverse calls per view on camera matrices (each a device-wide host synchronisation) are cached on the
+    scene / camera objects for as long as the matrices are the same unmodified tensors;
   * the depth-to-normal map (utils/graphics_utils.py:38-75 through render_normal, :15-26) is one CUDA kernel per direction
     (csrc/depth_normal.cu) instead of ~12 + ~25 elementwise torch kernels.
 
@@ -57,6 +59,22 @@ def _prologue(pc, cam, learnt_normal, with_map):
     opacity, scales, rotations = fused.gaussian_prologue(pc._xyz, pc._opacity, pc._scaling, pc._rotation,
                                                          pc._features_dc, pc._features_rest, concat_sh=False)
     return opacity, scales, rotations, None
+
+
+def _cached_inverse(owner, attr, t, transposed=False):
+    """torch.inverse(t) (or of t.T), cached on `owner` for as long as `t` is the same unmodified tensor.  Camera poses are constants of
+    a training run; torch.inverse on CUDA tensors synchronises the device with the host (its error check reads `info`
+    back), and the reference evaluates two of them per render() call (gaussian_renderer/__init__.py:258-260)."""
+    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
+    hit = getattr(owner, attr, None)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    inv = torch.inverse(t.T if transposed else t)
+    try:
+        setattr(owner, attr, (key, inv))
+    except Exception:      # objects that refuse new attributes: no cache
+        pass
+    return inv
 
 
 def _empty_sources(cam):
@@ -188,8 +206,9 @@ def render(viewpoint_camera, pc, scene, pipe, args, bg_color, learnt_normal: boo
             else:
                 src_rendered_depths = scene.rendered_depth_list[selected]
             world_to_src = scene.world_view_transforms[selected]
-            src_to_world = torch.inverse(world_to_src)
-            ref_to_world = viewpoint_camera.world_view_transform.T.inverse()
+            src_to_world = _cached_inverse(scene, "_ibgs_b200_view_to_world", scene.world_view_transforms)[selected]
+            ref_to_world = _cached_inverse(viewpoint_camera, "_ibgs_b200_cam_to_world", viewpoint_camera.world_view_transform,
+                                           transposed=True)
             ref_to_src_list = (world_to_src @ ref_to_world.unsqueeze(0)).cuda()
             src_cam_pos = src_to_world[:, :3, 3].cuda()
             src_rendered_depths = src_rendered_depths.cuda()

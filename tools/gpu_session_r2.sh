@@ -8,9 +8,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 timeout 700 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> $OUT/${TAG}_pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
-timeout 700 python bench.py > $OUT/${TAG}_bench_b200.json 2> $OUT/${TAG}_bench_b200.err
+( time timeout 700 python bench.py > $OUT/${TAG}_bench_b200.json 2> $OUT/${TAG}_bench_b200.err ) 2> $OUT/${TAG}_bench_b200.time
 cp $OUT/${TAG}_bench_b200.json $OUT/${TAG}_bench_1gpu.json
-timeout 700 python bench.py --impl reference > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
+( time timeout 700 python bench.py --impl reference > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err ) 2> $OUT/${TAG}_bench_ref.time
 timeout 300 python tools/quick_ab.py cfg3_1080p --iters 10 > $OUT/${TAG}_ab_cfg3_1080p.log 2>&1
 timeout 300 python tools/quick_ab.py cfg2 --iters 10 > $OUT/${TAG}_ab_cfg2.log 2>&1
 timeout 300 python tools/quick_ab.py cfg3_1080p --iters 10 --depth-batch 4 > $OUT/${TAG}_depth_batch.log 2>&1

@@ -18,7 +18,7 @@ from typing import NamedTuple, Optional
 import torch
 
 from . import _native as N
-from .diff_plane_rasterization import _Allocator, _f32c, _ptr
+from .diff_plane_rasterization import _Allocator, _f32c, _poisoned_empty, _ptr
 
 
 class DepthBatchSettings(NamedTuple):
@@ -74,7 +74,7 @@ def render_depth_batch(settings: DepthBatchSettings, means3D, opacities, scales=
     keep = [_f32c(t, device) for t in (means3D, opacities, scales, rotations, cov3D_precomp, all_maps, normals,
                                        offsets, camera_centers)]
     # zeros: with P == 0 (or an empty view) the untouched planes must read as 0 like the reference's outputs
-    depths = (torch.zeros if P == 0 else torch.empty)((V, 1, H, W), dtype=torch.float32, device=device)
+    depths = (torch.zeros if P == 0 else _poisoned_empty)((V, 1, H, W), dtype=torch.float32, device=device)
     radii = torch.zeros((V, P), dtype=torch.int32, device=device) if return_radii else None
     counts = (C.c_int64 * V)()
     alloc = _Allocator(device)

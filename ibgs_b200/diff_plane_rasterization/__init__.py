@@ -13,12 +13,26 @@ PyTorch fallback: without libibgs_b200.so the import fails.
 from typing import NamedTuple
 
 import ctypes as C
+import os
 import torch
 import torch.nn as nn
 
 from .. import _native as N
 
 # tests flip this to keep the forward scratch (unsorted / sorted keys) alive for bit-exact comparison
+# IBGS_POISON_OUTPUTS=1 (debugging aid): every tensor the kernels are trusted to write COMPLETELY -- outputs, gradients, state
+# and scratch buffers, all allocated with torch.empty -- is pre-filled with NaN / 0xFF bytes, so a word a kernel fails to
+# write shows up in any comparison instead of depending on what the caching allocator handed out.
+POISON = os.environ.get("IBGS_POISON_OUTPUTS", "") not in ("", "0")
+
+
+def _poisoned_empty(shape, **kw):
+    t = torch.empty(shape, **kw)
+    if POISON and t.numel():
+        t.view(torch.uint8).fill_(0xFF) if t.dtype != torch.float32 else t.fill_(float("nan"))
+    return t
+
+
 KEEP_STATE = False
 LAST_STATE = {}
 
@@ -85,6 +99,8 @@ class _Allocator:
     def _alloc(self, user, which, nbytes):
         try:
             t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=self.device)
+            if POISON:
+                t.fill_(0xFF)
             if which == N.IBGS_BUF_SCRATCH:
                 self.scratch.append(t)
             else:
@@ -157,7 +173,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # leave unused slots untouched.  In render_geo mode our tile renderer writes every word of every output
         # (zeros included) and preprocess writes every radius, so torch.empty is enough; in the other modes the
         # untouched outputs must read as zeros.  (Separate tensors on purpose: callers keep single outputs alive.)
-        make = torch.empty if (rs.render_geo and P > 0) else torch.zeros
+        make = _poisoned_empty if (rs.render_geo and P > 0) else torch.zeros
         fopt = dict(dtype=torch.float32, device=device)
         iopt = dict(dtype=torch.int32, device=device)
         color = make((3, H, W), **fopt)
@@ -290,18 +306,19 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_normal = g_depth = g_warped = None
 
         # every row is written by the kernel (zeros for culled Gaussians) -> no memset needed
-        dL_dmeans3D = torch.empty((P, 3), **fopt)
-        dL_dmeans2D = torch.empty((P, 3), **fopt)
-        dL_dmeans2D_abs = torch.empty((P, 3), **fopt)
-        dL_dcolors = torch.empty((P, 3), **fopt)
-        dL_dall_map = torch.empty((P, 5), **fopt)
-        dL_dopacity = torch.empty((P, 1), **fopt)
+        E = _poisoned_empty
+        dL_dmeans3D = E((P, 3), **fopt)
+        dL_dmeans2D = E((P, 3), **fopt)
+        dL_dmeans2D_abs = E((P, 3), **fopt)
+        dL_dcolors = E((P, 3), **fopt)
+        dL_dall_map = E((P, 5), **fopt)
+        dL_dopacity = E((P, 1), **fopt)
         need_cov = cov3Ds_precomp.numel() != 0
-        dL_dcov3D = torch.empty((P, 6), **fopt) if need_cov else torch.zeros((0,), **fopt)
-        dL_dsh = torch.empty((P, 1 if split_sh else M_sh, 3), **fopt)
-        dL_dsh_rest = torch.empty((P, M_sh - 1, 3), **fopt) if split_sh else None
-        dL_dscales = torch.empty((P, 3), **fopt)
-        dL_drotations = torch.empty((P, 4), **fopt)
+        dL_dcov3D = E((P, 6), **fopt) if need_cov else torch.zeros((0,), **fopt)
+        dL_dsh = E((P, 1 if split_sh else M_sh, 3), **fopt)
+        dL_dsh_rest = E((P, M_sh - 1, 3), **fopt) if split_sh else None
+        dL_dscales = E((P, 3), **fopt)
+        dL_drotations = E((P, 4), **fopt)
 
         accumulated = set()   # inputs whose gradient the kernel added into .grad: autograd gets None for them
         if P != 0:

@@ -42,7 +42,29 @@ def _share_depth_cache(wo, wr):
     wo.scene.rendered_depth_list.copy_(wr.scene.rendered_depth_list)
 
 
+def _describe(po, pr):
+    """One line per output for a failing comparison: which side holds non-finite values, how many entries differ."""
+    lines = []
+    for k in ("radii", "visibility_filter", "use_first_src_frame_mask") + FLOAT_KEYS + ("median_intersected_depth_normal",):
+        a, b = po.get(k), pr.get(k)
+        if a is None or b is None:
+            lines.append(f"{k}: ours {None if a is None else tuple(a.shape)} / reference {None if b is None else tuple(b.shape)}")
+            continue
+        af, bf = a.float(), b.float()
+        d = (af - bf).abs()
+        lines.append(f"{k}: max|d| {d.max().item():.3e}  differing entries {(d > 1e-4).float().mean().item():.2e}  "
+                     f"non-finite ours {(~torch.isfinite(af)).sum().item()} / reference {(~torch.isfinite(bf)).sum().item()}")
+    return "\n".join(lines)
+
+
 def _compare_pkg(po, pr, tol=1e-4):
+    try:
+        _compare_pkg_checks(po, pr, tol)
+    except AssertionError as ex:
+        raise AssertionError(f"{ex}\n--- all outputs, this repo vs reference ---\n{_describe(po, pr)}") from None
+
+
+def _compare_pkg_checks(po, pr, tol=1e-4):
     assert torch.equal(po["radii"], pr["radii"])
     assert torch.equal(po["visibility_filter"], pr["visibility_filter"])
     assert torch.equal(po["use_first_src_frame_mask"], pr["use_first_src_frame_mask"])

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define IBGS_ABI_VERSION 4
+#define IBGS_ABI_VERSION 5   /* 5: IbgsPrologueArgs.smallest_axis_normal; colour-feature, NHWC-glue and depth-normal entry points */
 
 /* Compile-time constants of the reference (cuda_rasterizer/config.h:15-19, auxiliary.h:21-23). */
 #define IBGS_NUM_CHANNELS 3

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(N.lib, n), f"{n} declared in include/ibgs_b200.h but not exported"
     assert sorted(N.EXPORTS) == names
-    assert N.lib.ibgs_abi_version() == 4
+    assert N.lib.ibgs_abi_version() == 5
 
 
 def test_struct_layouts_match_header(tmp_path):

@@ -65,13 +65,12 @@ def _cached_inverse(owner, attr, t, transposed=False):
     """torch.inverse(t) (or of t.T), cached on `owner` for as long as `t` is the same unmodified tensor.  Camera poses are constants of
     a training run; torch.inverse on CUDA tensors synchronises the device with the host (its error check reads `info`
     back), and the reference evaluates two of them per render() call (gaussian_renderer/__init__.py:258-260)."""
-    key = (t.data_ptr(), t._version, tuple(t.shape), str(t.device))
     hit = getattr(owner, attr, None)
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    if hit is not None and hit[0] is t and hit[1] == t._version:      # the very same tensor object, not written since
+        return hit[2]
     inv = torch.inverse(t.T if transposed else t)
     try:
-        setattr(owner, attr, (key, inv))
+        setattr(owner, attr, (t, t._version, inv))     # holds `t`: its storage cannot be recycled under the cache
     except Exception:      # objects that refuse new attributes: no cache
         pass
     return inv

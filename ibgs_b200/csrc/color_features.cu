@@ -12,8 +12,11 @@
 // shared memory (packed FP32: two views of a pixel per FFMA2), and the conv decoder's input leaves in its final layout --
 // NHWC, channel count padded to a multiple of 8, optionally bf16 -- so the tensor-core convolutions that follow need
 // no layout or dtype conversion pass.  The backward recomputes the hidden layers (nothing but the inputs is saved) and
-// forms the weight gradients per warp in registers (lane j owns column j of dW2: the warp's 32 pixels are staged in
-// shared memory and every lane walks them) before one atomicAdd per (warp, weight).
+// forms the weight gradients per warp in registers: the warp's 32 pixels are staged in a shared-memory tile and every lane
+// walks them -- pass A: lane j accumulates column j of dW2 = g2 (x) h1; pass B (the g2 rows overwritten by g1): row j of
+// dW1 = g1 (x) x -- with the matrix products in packed FP32 (two outputs per FFMA2 from the register pair an LDS.128
+// delivers); the block's four warps are summed through shared memory and there is one atomicAdd per (block, weight).
+// 128 registers, 10 KB of tile per warp -> 4 CTAs / SM (ncu: bound by shared-memory latency, not by issue slots).
 //
 // Algorithmic bytes per pixel (V views): forward 4*(7V + 6) in, 2*CP (bf16) out; backward the same in + 2*CP, 4*(3V + 3) out.
 #include "common.cuh"

@@ -116,7 +116,7 @@ MAX_DEPTH_BATCH = 16
 
 EXPORTS = [
     "ibgs_forward", "ibgs_backward", "ibgs_mark_visible", "ibgs_dist2_scratch_bytes", "ibgs_dist2",
-    "ibgs_forward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
+    "ibgs_forward_h", "ibgs_forward_backward_h", "ibgs_dist2_h", "ibgs_state_layout", "ibgs_sort_bits", "ibgs_last_error",
     "ibgs_abi_version", "ibgs_launch_count", "ibgs_release_cached", "ibgs_profile_enable", "ibgs_profile_reset",
     "ibgs_profile_read", "ibgs_profile_name", "ibgs_profile_stages", "ibgs_prologue_forward",
     "ibgs_prologue_backward", "ibgs_forward_depth_batch", "ibgs_ssim_forward", "ibgs_ssim_backward", "ibgs_adam_step", "ibgs_set_backward_variant", "ibgs_set_forward_variant",
@@ -146,6 +146,8 @@ def _load():
     lib.ibgs_dist2.argtypes = [C.c_int32, _fp, _fp, _fp, C.c_size_t, C.c_void_p]
     lib.ibgs_forward_h.restype = C.c_int64
     lib.ibgs_forward_h.argtypes = [C.POINTER(IbgsForwardArgs)]
+    lib.ibgs_forward_backward_h.restype = C.c_int64
+    lib.ibgs_forward_backward_h.argtypes = [C.POINTER(IbgsForwardArgs), C.POINTER(IbgsBackwardArgs)]
     lib.ibgs_dist2_h.restype = C.c_int
     lib.ibgs_dist2_h.argtypes = [C.c_int32, _fp, _fp]
     lib.ibgs_state_layout.restype = C.c_int

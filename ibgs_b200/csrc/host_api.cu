@@ -1,11 +1,13 @@
-// host_api.cu -- host-buffer convenience entry points (ibgs_forward_h, ibgs_dist2_h).
+// host_api.cu -- host-buffer convenience entry points (ibgs_forward_h, ibgs_forward_backward_h, ibgs_dist2_h).
 //
 // What a caller without a device allocator binds (cgo / JNI / ctypes on plain host arrays): every
 // pointer in the argument struct is a HOST pointer; inputs are staged to the device, the device entry
 // point runs on a private stream, outputs are copied back before returning.  State buffers are freed
-// on return, so this path is forward / inference only (reference analogue: render.py's no_grad loop,
-// render.py:297).
+// on return: ibgs_forward_h is the inference call (reference analogue: render.py's no_grad loop,
+// render.py:297); ibgs_forward_backward_h runs one training view -- forward, then backward with the
+// caller's cotangents while the state is still on the device -- and returns outputs and gradients.
 #include "common.cuh"
+#include <cstring>
 #include <vector>
 
 namespace {
@@ -34,9 +36,16 @@ struct DevPool {
   }
 };
 
+struct HostCall {
+  DevPool pool;
+  void* state[4] = {nullptr, nullptr, nullptr, nullptr};   // last GEOM / BINNING / IMAGE buffer handed to the library
+};
+
 void* pool_alloc(void* user, int which, size_t bytes) {
-  (void)which;
-  return ((DevPool*)user)->get(bytes);
+  HostCall* c = (HostCall*)user;
+  void* p = c->pool.get(bytes);
+  if (which == IBGS_BUF_GEOM || which == IBGS_BUF_BINNING || which == IBGS_BUF_IMAGE) c->state[which & 3] = p;
+  return p;
 }
 
 template <typename T>
@@ -46,19 +55,18 @@ struct Out {
   size_t count;
 };
 
-}  // namespace
 
-extern "C" int64_t ibgs_forward_h(IbgsForwardArgs* h) {
-  if (!h) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
-  DevPool pool;
-  CUDA_TRY(cudaStreamCreateWithFlags(&pool.s, cudaStreamNonBlocking));
+// stages the forward's host inputs, allocates device outputs, runs ibgs_forward on call.pool.s and queues the copies of the
+// outputs back to the host; `d` keeps the device-side argument struct for a backward that may follow
+int64_t forward_staged(HostCall& call, IbgsForwardArgs* h, IbgsForwardArgs& d) {
+  DevPool& pool = call.pool;
   const size_t P = (size_t)h->P;
   const IbgsView& hv = h->view;
   const size_t N = (size_t)hv.image_width * hv.image_height;
   const size_t nb = (size_t)hv.nb_src_images;
   const size_t M = (size_t)hv.sh_coeffs;
 
-  IbgsForwardArgs d = *h;
+  d = *h;
   d.view.bg = pool.up(hv.bg, 3);
   d.view.viewmatrix = pool.up(hv.viewmatrix, 16);
   d.view.projmatrix = pool.up(hv.projmatrix, 16);
@@ -86,12 +94,12 @@ extern "C" int64_t ibgs_forward_h(IbgsForwardArgs* h) {
                                    {h->out_camera_ray, nullptr, 3 * N}};
   for (auto& o : fouts) {
     o.dev = (float*)pool.get(o.count * sizeof(float));
-    if (!o.dev) { pool.release(); ibgs_set_error("device allocation failed"); return IBGS_EALLOC; }
+    if (!o.dev) { ibgs_set_error("device allocation failed"); return IBGS_EALLOC; }
     cudaMemsetAsync(o.dev, 0, o.count * sizeof(float), pool.s);
   }
   int32_t* radii_d = (int32_t*)pool.get((P ? P : 1) * sizeof(int32_t));
   int32_t* mask_d = (int32_t*)pool.get(N * sizeof(int32_t));
-  if (!radii_d || !mask_d) { pool.release(); ibgs_set_error("device allocation failed"); return IBGS_EALLOC; }
+  if (!radii_d || !mask_d) { ibgs_set_error("device allocation failed"); return IBGS_EALLOC; }
   cudaMemsetAsync(radii_d, 0, (P ? P : 1) * sizeof(int32_t), pool.s);
   cudaMemsetAsync(mask_d, 0, N * sizeof(int32_t), pool.s);
   d.out_color = fouts[0].dev;
@@ -104,7 +112,7 @@ extern "C" int64_t ibgs_forward_h(IbgsForwardArgs* h) {
   d.radii = radii_d;
   d.out_use_first_src_frame = mask_d;
   d.alloc = pool_alloc;
-  d.alloc_user = &pool;
+  d.alloc_user = &call;
 
   int64_t R = ibgs_forward(&d, pool.s);
   if (R >= 0) {
@@ -113,15 +121,95 @@ extern "C" int64_t ibgs_forward_h(IbgsForwardArgs* h) {
     if (h->radii) cudaMemcpyAsync(h->radii, radii_d, P * sizeof(int32_t), cudaMemcpyDeviceToHost, pool.s);
     if (h->out_use_first_src_frame)
       cudaMemcpyAsync(h->out_use_first_src_frame, mask_d, N * sizeof(int32_t), cudaMemcpyDeviceToHost, pool.s);
-  }
-  pool.release();
-  cudaError_t e = cudaStreamSynchronize(pool.s);
-  cudaStreamDestroy(pool.s);
-  if (R >= 0 && e != cudaSuccess) {
-    ibgs_set_error("ibgs_forward_h: %s", cudaGetErrorString(e));
-    return IBGS_ECUDA;
+    h->tex_generation_out = d.tex_generation_out;
+    h->scratch_capacity_out = d.scratch_capacity_out;
   }
   return R;
+}
+
+int64_t finish(HostCall& call, int64_t rc, const char* who) {
+  call.pool.release();
+  cudaError_t e = cudaStreamSynchronize(call.pool.s);
+  cudaStreamDestroy(call.pool.s);
+  if (rc >= 0 && e != cudaSuccess) {
+    ibgs_set_error("%s: %s", who, cudaGetErrorString(e));
+    return IBGS_ECUDA;
+  }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" int64_t ibgs_forward_h(IbgsForwardArgs* h) {
+  if (!h) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
+  HostCall call;
+  CUDA_TRY(cudaStreamCreateWithFlags(&call.pool.s, cudaStreamNonBlocking));
+  IbgsForwardArgs d;
+  const int64_t R = forward_staged(call, h, d);
+  return finish(call, R, "ibgs_forward_h");
+}
+
+extern "C" int64_t ibgs_forward_backward_h(IbgsForwardArgs* h, IbgsBackwardArgs* hb) {
+  if (!h || !hb) { ibgs_set_error("args is NULL"); return IBGS_EINVAL; }
+  if (!hb->dL_dout_color) { ibgs_set_error("dL_dout_color must be given"); return IBGS_EINVAL; }
+  HostCall call;
+  CUDA_TRY(cudaStreamCreateWithFlags(&call.pool.s, cudaStreamNonBlocking));
+  DevPool& pool = call.pool;
+  IbgsForwardArgs d;
+  const int64_t R = forward_staged(call, h, d);
+  if (R < 0 || h->P == 0) return finish(call, R, "ibgs_forward_backward_h");
+
+  const size_t P = (size_t)h->P;
+  const size_t N = (size_t)h->view.image_width * h->view.image_height;
+  const size_t M = (size_t)h->view.sh_coeffs;
+  const bool split = h->shs_rest != nullptr;
+  IbgsBackwardArgs b;
+  memset(&b, 0, sizeof(b));
+  b.P = h->P;
+  b.R = R;
+  b.view = d.view;
+  b.means3D = d.means3D; b.shs = d.shs; b.shs_rest = d.shs_rest; b.colors_precomp = d.colors_precomp;
+  b.scales = d.scales; b.rotations = d.rotations; b.cov3D_precomp = d.cov3D_precomp; b.all_map = d.all_map;
+  b.radii = d.radii;
+  b.out_median_intersected_depth = d.out_median_intersected_depth;
+  b.out_warped_image = d.out_warped_image;
+  b.geom_buffer = call.state[IBGS_BUF_GEOM & 3];
+  b.binning_buffer = call.state[IBGS_BUF_BINNING & 3];
+  b.image_buffer = call.state[IBGS_BUF_IMAGE & 3];
+  b.tex_generation = d.tex_generation_out;
+  b.dL_dout_color = pool.up(hb->dL_dout_color, 3 * N);
+  b.dL_dout_normal_map = pool.up(hb->dL_dout_normal_map, 3 * N);
+  b.dL_dout_median_intersected_depth = pool.up(hb->dL_dout_median_intersected_depth, N);
+  b.dL_dout_warped_image = pool.up(hb->dL_dout_warped_image, 3 * MAX_SRC * N);
+  if (h->view.render_geo && (!b.dL_dout_normal_map || !b.dL_dout_median_intersected_depth || !b.dL_dout_warped_image)) {
+    ibgs_set_error("render_geo needs the normal / depth / warped cotangents");
+    return finish(call, IBGS_EINVAL, "ibgs_forward_backward_h");
+  }
+  const size_t sh_rows = split ? 1 : M;
+  std::vector<Out<float>> gouts = {{hb->dL_dmeans3D, nullptr, P * 3},        {hb->dL_dmeans2D, nullptr, P * 3},
+                                   {hb->dL_dmeans2D_abs, nullptr, P * 3},    {hb->dL_dcolors, nullptr, P * 3},
+                                   {hb->dL_dopacity, nullptr, P},            {hb->dL_dcov3D, nullptr, h->cov3D_precomp ? P * 6 : 0},
+                                   {hb->dL_dsh, nullptr, M ? P * sh_rows * 3 : 0},
+                                   {hb->dL_dsh_rest, nullptr, split ? P * (M - 1) * 3 : 0},
+                                   {hb->dL_dscales, nullptr, P * 3},         {hb->dL_drotations, nullptr, P * 4},
+                                   {hb->dL_dall_map, nullptr, P * 5}};
+  for (auto& o : gouts) {
+    if (!o.count) continue;
+    o.dev = (float*)pool.get(o.count * sizeof(float));
+    if (!o.dev) { ibgs_set_error("device allocation failed"); return finish(call, IBGS_EALLOC, "ibgs_forward_backward_h"); }
+  }
+  b.dL_dmeans3D = gouts[0].dev; b.dL_dmeans2D = gouts[1].dev; b.dL_dmeans2D_abs = gouts[2].dev; b.dL_dcolors = gouts[3].dev;
+  b.dL_dopacity = gouts[4].dev; b.dL_dcov3D = gouts[5].dev; b.dL_dsh = gouts[6].dev; b.dL_dsh_rest = gouts[7].dev;
+  b.dL_dscales = gouts[8].dev; b.dL_drotations = gouts[9].dev; b.dL_dall_map = gouts[10].dev;
+  b.alloc = pool_alloc;
+  b.alloc_user = &call;
+  b.accumulate_mask = 0;
+  int rc = ibgs_backward(&b, pool.s);
+  if (rc == IBGS_OK) {
+    for (auto& o : gouts)
+      if (o.host && o.dev) cudaMemcpyAsync(o.host, o.dev, o.count * sizeof(float), cudaMemcpyDeviceToHost, pool.s);
+  }
+  return finish(call, rc == IBGS_OK ? R : rc, "ibgs_forward_backward_h");
 }
 
 extern "C" int ibgs_dist2_h(int32_t P, const float* points_host, float* mean_dists_host) {

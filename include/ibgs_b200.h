@@ -368,6 +368,10 @@ int ibgs_depth_normal_backward(const float* depth, const float* g_normal, float*
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages
  * through its own device arena (cudaMallocAsync) and copies results back before returning. */
 int64_t ibgs_forward_h(IbgsForwardArgs* host_args);
+/* One training view with host buffers: the forward above, then ibgs_backward with the host cotangents of `host_bw`
+ * (dL_dout_*) while the state is still on the device; every non-NULL dL_d* of `host_bw` receives its gradient.  Only the
+ * cotangent and gradient pointers of `host_bw` are read (its inputs are the forward's).  Returns num_rendered. */
+int64_t ibgs_forward_backward_h(IbgsForwardArgs* host_args, IbgsBackwardArgs* host_bw);
 int ibgs_dist2_h(int32_t P, const float* points_host, float* mean_dists_host);
 
 /* The binning stage's own device primitives (csrc/sort.cu; they replace cub::DeviceRadixSort::SortPairs /

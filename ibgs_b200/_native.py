@@ -124,7 +124,7 @@ EXPORTS = [
     "ibgs_color_features_forward", "ibgs_color_features_backward",
     "ibgs_nhwc_maxpool2_forward", "ibgs_nhwc_maxpool2_backward", "ibgs_nhwc_upsample_cat_forward",
     "ibgs_nhwc_upsample_backward", "ibgs_nhwc_relu_bias_backward",
-    "ibgs_depth_normal_forward", "ibgs_depth_normal_backward",
+    "ibgs_depth_normal_forward", "ibgs_depth_normal_backward", "ibgs_densification_stats",
 ]
 
 
@@ -191,6 +191,8 @@ def _load():
     lib.ibgs_depth_normal_forward.argtypes = [_fp, _fp, i32, i32, f32, f32, f32, f32, C.c_void_p]
     lib.ibgs_depth_normal_backward.restype = C.c_int
     lib.ibgs_depth_normal_backward.argtypes = [_fp, _fp, _fp, i32, i32, f32, f32, f32, f32, C.c_void_p]
+    lib.ibgs_densification_stats.restype = C.c_int
+    lib.ibgs_densification_stats.argtypes = [i32] + [_fp] * 8 + [C.c_void_p]
     lib.ibgs_nhwc_relu_bias_backward.restype = C.c_int
     lib.ibgs_nhwc_relu_bias_backward.argtypes = [_fp, i32, _fp, _fp, _fp, C.c_int64, i32, i32, C.c_void_p]
     for fn in (lib.ibgs_set_backward_variant, lib.ibgs_set_forward_variant):

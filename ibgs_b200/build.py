@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libibgs_b200.so")
 SOURCES = ["api.cu", "host_api.cu", "preprocess.cu", "binning.cu", "sort.cu", "textures.cu", "render_forward.cu",
-           "render_backward.cu", "preprocess_backward.cu", "knn.cu", "prologue.cu", "ssim.cu", "adam.cu", "color_features.cu", "nhwc_ops.cu", "depth_normal.cu"]
+           "render_backward.cu", "preprocess_backward.cu", "knn.cu", "prologue.cu", "ssim.cu", "adam.cu", "color_features.cu", "nhwc_ops.cu", "depth_normal.cu", "densify_stats.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "ibgs_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=true / precise div+sqrt are nvcc defaults, i.e. exactly the reference's flags (DPR/setup.py:21-29);

@@ -363,6 +363,15 @@ int ibgs_depth_normal_forward(const float* depth, float* normal, int32_t H, int3
 int ibgs_depth_normal_backward(const float* depth, const float* g_normal, float* g_depth, int32_t H, int32_t W, float fx,
                                float fy, float cx, float cy, void* stream);
 
+/* Per-view densification statistics (train.py:399-405 + GaussianModel.add_densification_stats,
+ * scene/gaussian_model.py:600-604; optional fast path), for the Gaussians with radii > 0: max_radii2D = max(max_radii2D,
+ * radii); xyz_gradient_accum += |viewspace_grad[:, :2]|; xyz_gradient_accum_abs += |viewspace_grad_abs[:, :2]|; denom += 1;
+ * denom_abs += 1.  viewspace_grad / _abs are the [P,3] gradients of the two screen-space dummy tensors; the five
+ * statistics arrays hold P floats each and are updated in place. */
+int ibgs_densification_stats(int32_t P, const int32_t* radii, const float* viewspace_grad, const float* viewspace_grad_abs,
+                             float* max_radii2D, float* xyz_gradient_accum, float* xyz_gradient_accum_abs, float* denom,
+                             float* denom_abs, void* stream);
+
 /* Host-buffer convenience entry points (what a non-torch caller binds -- cgo / JNI / ctypes on plain host arrays;
  * exercised by tests/test_gpu_host_api.py against the device entry points):
  * identical semantics, but every pointer in the structs is a HOST pointer; the library stages

@@ -405,6 +405,9 @@ def fast_fns(precision="bf16", losses=True, renderer=True, color=True):
     if renderer:
         import ibgs_b200.gaussian_renderer as FR
         f.render = FR.render
+    if renderer:
+        import ibgs_b200.densify as FD
+        f.add_densification_stats = FD.add_densification_stats
     if color:
         import ibgs_b200.color_aggregation as CA
         f.fuse_color = functools.partial(CA.fuse_color, precision=precision)
@@ -436,7 +439,11 @@ def dp_train_step(w, cam_indices, views_total, fns=None, sync_stats=False):
     for ci in cam_indices:
         out = train_iteration(w, ci, fns=fns)
         if w.iteration < w.opt.densify_until_iter or sync_stats:     # train.py:399: only while densification is on
-            densification_stats(w, out)
+            if hasattr(fns, "add_densification_stats"):
+                with torch.no_grad():
+                    fns.add_densification_stats(w.gaussians, out["render_pkg"])
+            else:
+                densification_stats(w, out)
         outs.append(out)
     dp.all_reduce_grads(views_total=views_total)
     dp.sync_depth_cache(w.scene.rendered_depth_list, cam_indices)

@@ -130,3 +130,31 @@ def test_depth_normal_kernel_equals_torch_expressions(H, W):
     na.backward(cot)
     nb.backward(cot)
     assert U.rel_l2(da.grad, db.grad) <= 1e-4, U.rel_l2(da.grad, db.grad)
+
+
+def test_densification_stats_kernel_equals_reference_statements():
+    """ibgs_b200.densify.add_densification_stats (one launch) against train.py:399-405 executed with the reference's own
+    GaussianModel.add_densification_stats, over three views (statistics accumulate)."""
+    from ibgs_b200.densify import add_densification_stats
+    w = _world()
+    gm = w.gaussians
+    names = ("max_radii2D", "xyz_gradient_accum", "xyz_gradient_accum_abs", "denom", "denom_abs")
+    gm.max_radii2D = torch.zeros((w.P,), device="cuda")       # what densification leaves behind (gaussian_model.py:212)
+    base = {n: getattr(gm, n).clone() for n in names}
+    outs = []
+    for i in range(3):
+        out = G.train_iteration(w, i)
+        outs.append(out["render_pkg"])
+        w.gaussians.optimizer.zero_grad(set_to_none=True)
+    for pkg in outs:                                                     # the reference's statements
+        G.densification_stats(w, dict(render_pkg=pkg))
+    want = {n: getattr(gm, n).clone() for n in names}
+    for n in names:
+        getattr(gm, n).copy_(base[n])
+    for pkg in outs:
+        add_densification_stats(gm, pkg)
+    for n in names:
+        a, b = getattr(gm, n), want[n]
+        assert torch.allclose(a, b, rtol=1e-6, atol=0), (n, (a - b).abs().max().item())
+    assert torch.equal(gm.denom, want["denom"]) and torch.equal(gm.max_radii2D, want["max_radii2D"])
+    assert gm.denom.max().item() == 3.0

@@ -86,14 +86,15 @@ class _Opts:
     residual_resolution_scale = 1.0
 
 
-@pytest.mark.parametrize("exposure,burn,dead", [(False, 1.0, 0), (True, 1.0, 0), (False, 0.6, 0), (False, 1.0, 2)])
+@pytest.mark.parametrize("exposure,burn,dead,mode", [(False, 1.0, 0, "mean"), (True, 1.0, 0, "mean"), (False, 0.6, 0, "mean"),
+                                                     (False, 1.0, 2, "mean"), (False, 1.0, 0, "max")])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_fuse_color_vs_reference(exposure, burn, dead, precision):
+def test_fuse_color_vs_reference(exposure, burn, dead, mode, precision):
     """Whole fuse_color, fast path vs the reference's function on the same unchanged module: result dict and the
     gradients of a loss on image_pred with respect to the rasterizer outputs and every network parameter."""
     from ibgs_b200 import color_aggregation as CA
     H, W = 90, 134
-    CAN, net = _net(H, W)
+    CAN, net = _net(H, W, mode)
     opts = _Opts()
     opts.enable_exposure_correction = exposure
     pkg = CR.random_render_pkg(H, W, seed=17, device="cuda", dead_views=dead)

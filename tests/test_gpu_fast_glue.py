@@ -15,9 +15,9 @@ FLOAT_KEYS = ("render", "rendered_normal", "median_intersected_depth", "cam_feat
               "camera_ray")
 
 
-def _world(**kw):
+def _world(config="cfg1", **kw):
     g = G.bind("b200")
-    w = G.build_world(g, "cfg1", n_views=6, sc_cpu=S.make_scene("cfg1"), **kw)
+    w = G.build_world(g, config, n_views=6, sc_cpu=S.make_scene(config), **kw)
     G.prime_depth_cache(w)
     return w
 
@@ -158,3 +158,22 @@ def test_densification_stats_kernel_equals_reference_statements():
         assert torch.allclose(a, b, rtol=1e-6, atol=0), (n, (a - b).abs().max().item())
     assert torch.equal(gm.denom, want["denom"]) and torch.equal(gm.max_radii2D, want["max_radii2D"])
     assert gm.denom.max().item() == 3.0
+
+
+def test_fast_train_iteration_at_full_size():
+    """BASELINE config 2's size (500 k Gaussians at 1920x1080): the fast iteration against the unchanged glue -- losses to
+    bf16 accuracy, every gradient in direction and magnitude."""
+    w = _world("cfg2")
+    res = []
+    for fns in (None, G.fast_fns(precision="bf16")):
+        w.gaussians.optimizer.zero_grad(set_to_none=True)
+        w.color_net.zero_grad(set_to_none=True)
+        out = G.train_iteration(w, 1, fns=fns)
+        assert out["fusion"] is not None
+        res.append((out, {n: v.clone() for n, v in G.gaussian_grads(w).items()}))
+    (o0, g0), (o1, g1) = res
+    for k in ("loss", "image_loss", "normal_loss", "photometric_loss"):
+        a, b = o1[k].item(), o0[k].item()
+        assert abs(a - b) <= 3e-3 * max(1.0, abs(b)), (k, a, b)
+    for n in G.GAUSSIAN_PARAMS:
+        assert U.rel_l2(g1[n], g0[n]) <= 8e-2, (n, U.rel_l2(g1[n], g0[n]))

@@ -24,7 +24,19 @@ FLOAT_KEYS = ("render", "rendered_normal", "median_intersected_depth", "cam_feat
 def glues():
     if not G.reference_available():
         pytest.skip("baseline/_ref/py or oracle/_ref/dpr not staged (run __graft_entry__.build() where /root/reference exists)")
-    return G.bind("b200"), G.bind("reference")
+    gl = (G.bind("b200"), G.bind("reference"))
+    # One throw-away priming pass per binding before anything is compared.  The comparisons below are exact (the outputs
+    # of the two rasterizers are bit-identical on this scene), so they rely on the torch glue in front of them --
+    # get_normal, the `global_normal @ world_view_transform` product, torch.inverse ... -- producing bit-identical inputs in
+    # both worlds.  On a fresh process the FIRST execution of that glue occasionally differs in the last bit from every
+    # later one (library first-call algorithm selection; seen on ~1 fresh box in 10: a handful of median-depth selections
+    # flip, tools/flake_hunt.py), which is a property of neither rasterizer.
+    for g in gl:
+        w = G.build_world(g, "cfg1", n_views=6, sc_cpu=S.make_scene("cfg1"))
+        G.prime_depth_cache(w)
+        del w
+    torch.cuda.synchronize()
+    return gl
 
 
 def _worlds(glues, config="cfg1", n_views=6, **kw):

@@ -50,7 +50,10 @@ def _share_depth_cache(wo, wr):
     G.prime_depth_cache(wo)
     G.prime_depth_cache(wr)
     err = (wo.scene.rendered_depth_list - wr.scene.rendered_depth_list).abs().max().item()
-    assert err <= 1e-4, f"rendered_depth_list: {err}"
+    # (if this ever fails: were the two worlds' camera matrices -- torch bmm / inverse at Camera construction -- bit-equal?)
+    cams = [all(torch.equal(getattr(a, k), getattr(b, k)) for k in ("world_view_transform", "full_proj_transform", "camera_center"))
+            for a, b in zip(wo.scene.getTrainCameras(), wr.scene.getTrainCameras())]
+    assert err <= 1e-4, f"rendered_depth_list: {err}; camera matrices bit-equal per view: {cams}"
     wo.scene.rendered_depth_list.copy_(wr.scene.rendered_depth_list)
 
 

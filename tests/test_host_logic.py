@@ -166,3 +166,54 @@ def test_kernel_variant_knobs_validate_their_argument():
     for fn in (N.lib.ibgs_set_backward_variant, N.lib.ibgs_set_forward_variant):
         assert fn(7) < 0 and "pixels_per_lane" in N.last_error()
         assert fn(2) == 0 and fn(0) == 0
+
+
+def test_round2_fast_paths_fail_loudly_without_cuda_tensors_and_validate_arguments():
+    """The colour-aggregation / render / densification fast paths: no CPU fallback, argument errors before any launch."""
+    import types
+    import pytest
+    import torch
+    import ibgs_b200.color_aggregation as ca
+    import ibgs_b200.densify as dn
+    import ibgs_b200.gaussian_renderer as gr
+    from ibgs_b200 import _native as N
+    H, W = 8, 8
+    mlp = torch.nn.Sequential(torch.nn.Linear(7, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU())
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ca.color_features(torch.zeros(9, H, W), torch.zeros(12, H, W), torch.zeros(3, H, W), torch.zeros(3, H, W), mlp, 3)
+    net = types.SimpleNamespace(per_view_feat_dim=32, feat_aggregate_mode="mean", per_view_mlp=mlp, conv_decoder=None)
+    opts = types.SimpleNamespace(residual_resolution_scale=1.0, enable_exposure_correction=False, nb_visible_src_frames=3)
+    pkg = {}
+    with pytest.raises(ValueError):
+        ca.fuse_color(pkg, net, None, None, None, 1, opts, precision="fp8")
+    opts.residual_resolution_scale = 0.5
+    with pytest.raises(NotImplementedError):
+        ca.fuse_color(pkg, net, None, None, None, 1, opts)
+    opts.residual_resolution_scale = 1.0
+    net.per_view_feat_dim = 16
+    with pytest.raises(NotImplementedError):
+        ca.fuse_color(pkg, net, None, None, None, 1, opts)
+    assert ca.fuse_color(pkg, None, None, None, None, 1, opts) is None
+    for fn in (ca.max_pool2, lambda t: ca.upsample_nearest(t, (4, 4))):
+        with pytest.raises(RuntimeError):
+            fn(torch.zeros(1, 8, 4, 4))                     # CPU tensor
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        gr.depth_normal(types.SimpleNamespace(Fx=1.0, Fy=1.0, Cx=0.0, Cy=0.0), torch.ones(4, 4))
+    with pytest.raises(NotImplementedError):
+        gr.render(None, None, None, types.SimpleNamespace(convert_SHs_python=True, compute_cov3D_python=False), None, None,
+                  True, 4, 4)
+    gm = types.SimpleNamespace()
+    leaf = torch.zeros(4, 3, requires_grad=True)
+    with pytest.raises(RuntimeError, match="after loss.backward"):
+        dn.add_densification_stats(gm, dict(radii=torch.zeros(4, dtype=torch.int32), viewspace_points=leaf,
+                                            viewspace_points_abs=leaf))
+    # C ABI argument checks of the new entry points (no launch happens)
+    a = N.IbgsColorFeatArgs()
+    a.height, a.width, a.n_views, a.channel_pitch = 4, 4, 9, 40
+    assert N.lib.ibgs_color_features_forward(a, None) < 0 and "n_views" in N.last_error()
+    a.n_views, a.channel_pitch = 3, 38
+    assert N.lib.ibgs_color_features_forward(a, None) < 0 and "channel_pitch" in N.last_error()
+    assert N.lib.ibgs_nhwc_maxpool2_forward(None, None, None, 4, 4, 7, 1, None) < 0
+    assert N.lib.ibgs_depth_normal_forward(None, None, 4, 4, 1.0, 1.0, 0.0, 0.0, None) < 0
+    assert N.lib.ibgs_densification_stats(-1, None, None, None, None, None, None, None, None, None) < 0
+    assert N.lib.ibgs_forward_backward_h(None, None) < 0
